@@ -1,0 +1,297 @@
+"""CPU model of the *reformulated* algorithm the CUDA kernels implement (TEST INFRA ONLY).
+
+``oracle/ref_port.py`` restates the reference (tall SVDs, 384x768 per-sample SVDs,
+autograd).  The CUDA path computes the same numbers through cheaper, exact
+reformulations: token-space Grams, small symmetric eigenproblems, an
+N x N per-sample Procrustes problem and closed-form gradients.  This file states that
+reformulated algorithm, stage by stage, in plain torch so that
+
+  * each CUDA kernel has a stage-level expected output (tests/test_kernels_gpu.py), and
+  * the reformulation itself is proven against the reference's autograd on CPU
+    (tests/test_kernel_model.py) -- no GPU needed.
+
+Nothing under the shipped package imports this file.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+EPS32 = float(torch.finfo(torch.float32).eps)
+
+
+# ------------------------------------------------------------------ stage: statistics
+def token_stats(tokens: torch.Tensor):
+    """Gram and column sum in *token space* (kernel: basd_gram_colsum).
+    bf16 x bf16 products are exact in fp32, so this is exact up to accumulation order."""
+    x = tokens.reshape(-1, tokens.shape[-1]).float()
+    return x.T @ x, x.sum(dim=0)
+
+
+def rotate_stats(gram, colsum, proj):
+    """P G P^T and P c (kernels: sgemm)  -- reference: layer_selector.py:72,88."""
+    return proj @ gram @ proj.T, proj @ colsum
+
+
+def sym_eig_desc(mat: torch.Tensor):
+    """Symmetric eigendecomposition, eigenvalues descending (kernel: jacobi_eig)."""
+    lam, vec = torch.linalg.eigh(mat.double())
+    lam = lam.flip(0).float()
+    vec = vec.flip(1).float()
+    return lam, vec
+
+
+def mp_rank_from_spectrum(lam_desc: torch.Tensor, rows: int, dim_cap: int) -> int:
+    """MP rank from the spectrum of the uncentred second moment (kernel: mp_rank).
+    reference: layer_selector.py:8-20,74. Scale-free, so the 1/M factor is dropped."""
+    n = lam_desc.numel()
+    asc = lam_desc.flip(0)
+    median = asc[(n - 1) // 2]                      # torch.median: lower middle
+    edge = median * (1.0 + math.sqrt(n / rows)) ** 2
+    return min(int((lam_desc > edge).sum()), dim_cap)
+
+
+# ------------------------------------------------------------------ stage: selector
+def selector_model(student_stats, teacher_stats, rows_s, rows_t, proj_s, proj_t, log_temps):
+    """student_stats/teacher_stats: lists of (gram, colsum) in token space.
+    Returns dict with ranks, dist (E,L), weights (E,L) and what backward needs."""
+    d_s = proj_s.shape[0]
+    teach = []
+    for gram, col in teacher_stats:
+        g, c = rotate_stats(gram, col, proj_t)
+        lam_u, _ = sym_eig_desc(g)
+        k = mp_rank_from_spectrum(lam_u, rows_t, d_s - 1)
+        lam, vec = sym_eig_desc(g - torch.outer(c, c) / rows_t)
+        teach.append(dict(k=k, basis=vec[:, :k], sw=lam[:k].clamp(min=0).sqrt()))
+    temps = torch.nn.functional.softplus(log_temps)
+    out = dict(ranks=[t["k"] for t in teach], dist=[], weights=[], saved=[])
+    for i, (gram, col) in enumerate(student_stats):
+        g, c = rotate_stats(gram, col, proj_s)
+        lam, vec = sym_eig_desc(g - torch.outer(c, c) / rows_s)
+        dist = torch.zeros(len(teach))
+        per = []
+        for j, t in enumerate(teach):
+            k = t["k"]
+            full = vec.T @ t["basis"]                       # (D,k) = V_s^T U_t
+            ux, sig, vxt = torch.linalg.svd(full[:k].double())
+            ux, sig, vxt = ux.float(), sig.float(), vxt.float()
+            theta = torch.acos(sig.clamp(max=1.0 - EPS32))
+            dist[j] = (t["sw"] * theta ** 2).sum() / t["sw"].sum()
+            per.append(dict(full=full, ux=ux, sig=sig, vx=vxt.T, theta=theta))
+        w = torch.softmax(-dist / temps[i], dim=0)
+        out["dist"].append(dist)
+        out["weights"].append(w)
+        out["saved"].append(dict(lam=lam, vec=vec, per=per, colsum_tok=col))
+    out["teach"] = teach
+    out["temps"] = temps
+    return out
+
+
+def selector_backward_model(sel, d_weights, rows_s, proj_s, log_temps):
+    """Given dL/dweights (E,L): returns dL/dlog_temps (E,) and, per student layer, the
+    token-space matrix W' (D_s x D_s) with dL/dS += (S - 1 mean^T) W'.
+    Closed form of the SVD/eig backward: only cross-block terms."""
+    d_logt = torch.zeros_like(log_temps)
+    w_primes = []
+    temps = sel["temps"]
+    for i, saved in enumerate(sel["saved"]):
+        w = sel["weights"][i]
+        dist = sel["dist"][i]
+        dy = w * (d_weights[i] - (w * d_weights[i]).sum())          # softmax backward
+        d_dist = -dy / temps[i]
+        d_tau = (dy * dist).sum() / temps[i] ** 2
+        d_logt[i] = d_tau * torch.sigmoid(log_temps[i])             # softplus backward
+        lam, vec = saved["lam"], saved["vec"]
+        dim = lam.numel()
+        omega = torch.zeros(dim, dim)
+        for j, t in enumerate(sel["teach"]):
+            k, p = t["k"], saved["per"][j]
+            sw = t["sw"]
+            sig, theta = p["sig"], p["theta"]
+            live = (sig < 1.0 - EPS32).float()                      # clamp kills the grad
+            d_sig = d_dist[j] * (sw / sw.sum()) * 2 * theta * (-1.0 / (1 - sig ** 2).clamp(min=1e-30).sqrt()) * live
+            lower = p["full"][k:]                                   # V_perp^T U_t  (D-k, k)
+            block = (lower @ p["vx"]) * d_sig @ p["ux"].T           # (D-k, k)
+            gap = lam[:k].unsqueeze(0) - lam[k:].unsqueeze(1)       # lam_i - lam_j
+            omega[k:, :k] += block / gap
+        d_gram = vec @ omega @ vec.T
+        w_sym = d_gram + d_gram.T
+        w_primes.append(proj_s.T @ w_sym @ proj_s)
+    return d_logt, w_primes
+
+
+# ------------------------------------------------------------------ stage: mixing
+def _round_like(x, dtype):
+    return x.to(dtype).float()
+
+
+def interp_taps(n_src: int, n_dst: int):
+    """1-D linear, align_corners=False (reference: combined.py:12; relational.py:30)."""
+    idx = torch.arange(n_dst, dtype=torch.float32)
+    src = ((idx + 0.5) * (n_src / n_dst) - 0.5).clamp(min=0)
+    lo = src.floor().long().clamp(max=n_src - 1)
+    hi = (lo + 1).clamp(max=n_src - 1)
+    frac = src - lo.float()
+    return lo, hi, frac
+
+
+def mix_and_align(weights_row, teacher_stack, n_student):
+    """Mixed + aligned teacher tokens for one student layer (kernel: mix_interp).
+    fp32 arithmetic on the (exactly upcast) tokens -- layer_selector.py:110-111 then
+    combined.py:12 -- with ONE final rounding to the token dtype, which is how the
+    kernel stores its output (bf16 tokens -> bf16 aligned tokens)."""
+    dt = teacher_stack.dtype
+    mixed = (weights_row.view(-1, 1, 1, 1) * teacher_stack.float()).sum(dim=0)   # (B,N_t,D_t)
+    n_t = mixed.shape[1]
+    if n_t != n_student:
+        lo, hi, frac = interp_taps(n_t, n_student)
+        mixed = mixed[:, lo] * (1 - frac).view(1, -1, 1) + mixed[:, hi] * frac.view(1, -1, 1)
+    return _round_like(mixed, dt)
+
+
+def attn_rows(attn: torch.Tensor, has_cls: bool):
+    """Per-layer importance row (kernel: attn_rows) -- relational.py:22-27, before mixing.
+    fp32 attention maps only in the model (bf16 maps are handled in the kernel test)."""
+    a = attn.float()
+    return a[:, :, 0, 1:].mean(dim=1) if has_cls else a.mean(dim=(1, 2))
+
+
+def mix_importance(weights_row, rows_stack, n_student):
+    """(L,B,N_t) rows -> normalised (B,N_s) importance + pre-normalisation sum."""
+    mixed = (weights_row.view(-1, 1, 1) * rows_stack).sum(dim=0)
+    n_t = mixed.shape[1]
+    if n_t != n_student:
+        lo, hi, frac = interp_taps(n_t, n_student)
+        mixed = mixed[:, lo] * (1 - frac) + mixed[:, hi] * frac
+    total = mixed.sum(dim=1, keepdim=True)
+    return mixed / total, total
+
+
+# ------------------------------------------------------------------ stage: Procrustes
+def pivoted_cholesky(k: torch.Tensor, rel_tol: float = 1e-6):
+    """Diagonally pivoted (rank-revealing) Cholesky of a PSD matrix, stopping when the
+    largest remaining pivot drops below rel_tol * largest initial diagonal
+    (kernel: procrustes_factor).  Returns L (N x N, zero columns beyond the rank) with
+    L L^T ~= K."""
+    n = k.shape[0]
+    a = k.clone()
+    low = torch.zeros_like(k)
+    floor = rel_tol * a.diagonal().max()
+    for j in range(n):
+        diag = a.diagonal()
+        p = int(diag.argmax())
+        if not diag[p] > floor:
+            break
+        col = a[:, p] / diag[p].sqrt()
+        low[:, j] = col
+        a -= torch.outer(col, col)
+        a[p, :] = 0                      # exact zero of the eliminated row/col
+        a[:, p] = 0
+    return low
+
+
+def procrustes_sample(s_tok, t_tok, w, *, sv_floor: float = 1e-6, rel_tol: float = 1e-6):
+    """One sample. s_tok (N,Ds), t_tok (N,Dt) fp32, w (N,) normalised.
+    Returns value f = tr_s + tr_t - 2 nuc and the closed-form pieces of its gradient.
+
+    With K_s = A A^T = L_s L_s^T, K_t = B B^T = L_t L_t^T and X = L_s^T L_t = U S V^T the
+    singular values of the cross-covariance A^T B are those of X, and
+      d nuc/dA = Y_A A,  Y_A = (L_t V) S^+ (L_t V)^T ;   d nuc/dB = Y_B B,  Y_B = (L_s U) S^+ (L_s U)^T
+      diag(A polar(A^T B) B^T) = rowdot(L_s U, L_t V).
+    Only U comes out of the one-sided Jacobi sweep; V is recovered as the normalised rows
+    of U^T X (no inverse of any factor is ever formed)."""
+    root = w.sqrt().unsqueeze(1)
+    a = root * (s_tok - (w.unsqueeze(1) * s_tok).sum(0, keepdim=True))
+    b = root * (t_tok - (w.unsqueeze(1) * t_tok).sum(0, keepdim=True))
+    k_s, k_t = a @ a.T, b @ b.T
+    l_s, l_t = pivoted_cholesky(k_s, rel_tol), pivoted_cholesky(k_t, rel_tol)
+    x = l_s.T @ l_t
+    # one-sided Jacobi on the columns of X^T would give V; we rotate columns of X^T ... the
+    # kernel orthogonalises the columns of G = X^T (so G R = V S, R = U):
+    u, sig, _ = torch.linalg.svd(x.double())
+    u, sig = u.float(), sig.float()
+    keep = sig > sv_floor * sig.max()
+    rows = u.T @ x                                        # S V^T, row i has norm sig_i
+    norms = rows.norm(dim=1)
+    vt = torch.where(keep.unsqueeze(1), rows / norms.clamp(min=1e-30).unsqueeze(1), torch.zeros_like(rows))
+    inv_sig = torch.where(keep, 1.0 / sig.clamp(min=1e-30), torch.zeros_like(sig))
+    nuc = sig.sum()
+    f_a = l_t @ vt.T                                      # L_t V
+    f_b = (l_s @ u) * keep                                # L_s U
+    y_a = (f_a * inv_sig) @ f_a.T
+    y_b = (f_b * inv_sig) @ f_b.T
+    pi_diag = (f_b * f_a).sum(dim=1)
+    f = k_s.diagonal().sum() + k_t.diagonal().sum() - 2 * nuc
+    grad_s = 2 * root * (a - y_a @ a)                     # df/dS      (w held fixed)
+    grad_t = 2 * root * (b - y_b @ b)                     # df/dR'
+    grad_w = (k_s.diagonal() + k_t.diagonal() - 2 * pi_diag) / w   # df/dw (normalised w)
+    return f, grad_s, grad_t, grad_w
+
+
+# ------------------------------------------------------------------ whole step
+def full_step_model(logits, targets, students, teachers, attns, *, layers, proj_s, proj_t,
+                    log_temps, n_student, has_cls, criterion):
+    """Forward + hand-derived backward of the whole loss, assembled from the stages
+    above exactly as the CUDA host code assembles the kernels.
+    Returns dict(loss, ce, geo, ranks, weights, grad_students{layer}, grad_log_temps,
+    grad_logits)."""
+    t_keys = sorted(teachers.keys())
+    t_stack = torch.stack([teachers[k] for k in t_keys])              # (L,B,Nt,Dt)
+    n_l, bsz, n_t, d_t = t_stack.shape
+    rows_t = bsz * n_t
+    rows_s = bsz * students[layers[0]].shape[1]
+    sel = selector_model([token_stats(students[l]) for l in layers],
+                         [token_stats(teachers[k]) for k in t_keys],
+                         rows_s, rows_t, proj_s, proj_t, log_temps.detach())
+    rows = torch.stack([attn_rows(attns[k], has_cls) for k in t_keys])  # (L,B,Nt)
+
+    geo_terms, g_s, g_t, g_wt = [], {}, {}, {}
+    for i, layer in enumerate(layers):
+        w_mix = sel["weights"][i]
+        aligned = mix_and_align(w_mix, t_stack, n_student)
+        imp, total = mix_importance(w_mix, rows, n_student)
+        vals = []
+        gs = torch.zeros(bsz, n_student, students[layer].shape[2])
+        gt = torch.zeros(bsz, n_student, d_t)
+        gw = torch.zeros(bsz, n_student)
+        for b in range(bsz):
+            f, a_, b_, c_ = procrustes_sample(students[layer][b].float(), aligned[b].float(), imp[b])
+            vals.append(f)
+            gs[b], gt[b] = a_, b_
+            gw[b] = (c_ - f) / total[b]              # through w = w~/sum(w~): sum_n w_n df/dw_n = f
+        geo_terms.append(torch.stack(vals).mean())
+        g_s[layer], g_t[layer], g_wt[layer] = gs, gt, gw
+
+    logits = logits.detach().requires_grad_(True)
+    ce = criterion(logits, targets)
+    geo = torch.stack(geo_terms).mean()
+    inv = torch.stack([1.0 / ce.detach().clamp(min=EPS32), 1.0 / geo.clamp(min=EPS32)])
+    share = inv / inv.sum()
+    loss = share[0] * ce.detach() + share[1] * geo
+    (share[0] * ce).backward()
+
+    scale = share[1] / (len(layers) * bsz)           # dloss/df_{i,b}
+    d_weights = torch.zeros(len(layers), n_l)
+    grad_students = {}
+    for i, layer in enumerate(layers):
+        # teacher-token path: <dL/dR', A_interp T_l>; importance path: <dL/dw~, A_interp a_l>
+        if n_t != n_student:
+            lo, hi, frac = interp_taps(n_t, n_student)
+            up_tok = lambda z: z[:, lo] * (1 - frac).view(1, -1, 1) + z[:, hi] * frac.view(1, -1, 1)
+            up_row = lambda z: z[:, lo] * (1 - frac) + z[:, hi] * frac
+        else:
+            up_tok = up_row = lambda z: z
+        for j in range(n_l):
+            d_weights[i, j] = scale * ((g_t[layer] * up_tok(t_stack[j].float())).sum()
+                                       + (g_wt[layer] * up_row(rows[j])).sum())
+        grad_students[layer] = scale * g_s[layer]
+    d_logt, w_primes = selector_backward_model(sel, d_weights, rows_s, proj_s, log_temps.detach())
+    for i, layer in enumerate(layers):
+        x = students[layer].float().reshape(rows_s, -1)
+        centred = x - x.mean(dim=0, keepdim=True)
+        grad_students[layer] = grad_students[layer] + (centred @ w_primes[i]).reshape(bsz, n_student, -1)
+    return dict(loss=loss.detach(), ce=ce.detach(), geo=geo.detach(), ranks=sel["ranks"],
+                weights=torch.stack(sel["weights"]), dist=torch.stack(sel["dist"]),
+                grad_students=grad_students, grad_log_temps=d_logt, grad_logits=logits.grad,
+                d_weights=d_weights)
