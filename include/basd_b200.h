@@ -1,0 +1,155 @@
+/* basd_b200.h -- C ABI of the B200-native BASD loss hot path (libbasd_b200.so).
+ *
+ * The reference (indrajeetadityaroy9/vit-inductive-bias-distillation) has no FFI: its
+ * boundary is the Python module API of src/losses (combined.py:17-85,
+ * layer_selector.py:40-152, relational.py:5-50), whose arithmetic bottoms out in
+ * torch.linalg / torch.mm library calls.  This header is what a binding for that path
+ * binds instead: one entry point per device stage, each citing the reference lines it
+ * replaces.  The Python shim (vit-inductive-bias-distillation_b200/_native.py) loads the
+ * library with ctypes and calls these from a torch.autograd.Function.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is DEVICE memory unless marked "host";
+ *     the caller (torch) owns all buffers, nothing is allocated or freed inside;
+ *   - matrices are row-major; `ld` is the row pitch in elements, `stride` the distance
+ *     between consecutive problems of a batch in elements;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work, none
+ *     synchronises the host;
+ *   - return value: 0 on success, a cudaError_t (>0) if a launch failed, <0 for an
+ *     argument the kernels do not support.  No exceptions cross the boundary;
+ *   - dtype codes: BASD_DTYPE_F32 = 0, BASD_DTYPE_BF16 = 1.
+ */
+#ifndef BASD_B200_H
+#define BASD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BASD_DTYPE_F32 0
+#define BASD_DTYPE_BF16 1
+
+/* ---- dense contractions (fp32 SIMT; gemm_simt.cu) ---------------------------------- */
+
+/* C[b] = alpha * (*alpha_dev) * op(A[b]) * op(B[b]) + beta * C[b].  A may be bf16; when
+ * a_col_shift != NULL, a_col_shift[k] is subtracted from op(A)[m][k] on load (trans_a=0).
+ * Replaces torch.mm / torch.bmm at layer_selector.py:72,88,99 and relational.py:47 and the
+ * MmBackward/BmmBackward nodes of their autograd graph. */
+int basd_sgemm_batched(int trans_a, int trans_b, int M, int N, int K, const void* A, int a_dtype,
+                       int lda, long stride_a, const float* a_col_shift, const float* B, int ldb,
+                       long stride_b, float* C, int ldc, long stride_c, int batch, float alpha,
+                       const float* alpha_dev, float beta, void* stream);
+
+/* Token-space second-moment statistics of one (rows x D) token matrix:
+ * gram = X^T X (D x D, symmetric), colsum = X^T 1 (D).  Deterministic split-K.
+ * Replaces `features.T @ features` (layer_selector.py:13) and the column mean (:35,:91);
+ * the fixed projections proj_s/proj_t are applied to the small matrix afterwards. */
+long basd_token_gram_simt_workspace_floats(long rows, int D);
+int basd_token_gram_simt(const void* tokens, int dtype, long rows, int D, float* gram,
+                         float* colsum, float* workspace, void* stream);
+
+/* ---- small-matrix factorisations (jacobi.cu) ---------------------------------------- */
+
+/* Rank-revealing (diagonally pivoted) Cholesky of `batch` PSD matrices.  K is destroyed.
+ * LT row j holds the j-th column of L (K ~= LT^T LT); rows >= rank are zero.
+ * dims (optional, device) = active leading dimension per problem. */
+int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, float* LT, int ldl,
+                          long stride_l, int batch, float rel_tol, int* rank_out, const int* dims,
+                          void* stream);
+
+/* One-sided Jacobi: orthogonalises the rows of each (n x m) matrix in place (rows end up
+ * as sigma_j * v_j^T).  Shared-memory resident when the matrix fits, warp-shuffle dot
+ * products, in-register rotations.  Serves torch.linalg.eigvalsh (layer_selector.py:16),
+ * torch.linalg.svd (:36,:92), svdvals (:99) and matrix_norm(ord="nuc") (relational.py:48).
+ * Requires ld % 4 == 0, stride % 4 == 0, 16-byte aligned base, m <= 1024. */
+int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                     float tol, int max_sweeps, int* sweeps_out, void* stream);
+
+/* Row norms -> vals (norm or norm^2), unit rows -> V, optional descending sort. */
+int basd_rows_normalize(const float* G, int n, int m, int ld, long stride, float* V, int ldv,
+                        long stride_v, float* vals, int batch, int sort, int square,
+                        float rel_floor, const int* dims, void* stream);
+
+/* out[b*n + r] = <A[b][r,:], B[b][r,:]>  (Rayleigh-quotient refinement of eigenvalues). */
+int basd_rowdot(const float* A, int lda, long stride_a, const float* B, int ldb, long stride_b,
+                int n, int m, int batch, float* out, void* stream);
+
+/* ---- selector glue (selector.cu) ---------------------------------------------------- */
+
+/* K = sym(G) - inv_rows * colsum colsum^T (colsum may be NULL). layer_selector.py:35,91. */
+int basd_center_gram(const float* G, const float* colsum, int D, float inv_rows, float* K,
+                     int batch, void* stream);
+
+/* Device-side marchenko_pastur_rank (layer_selector.py:8-20) + the cap of :74.
+ * lam: (layers, D) spectrum of the uncentred second moment, any order.
+ * edges (optional): (layers, 2) = median, lambda_plus. No host sync. */
+int basd_mp_rank(const float* lam, int D, long rows, int cap, int* ranks, float* edges, int layers,
+                 void* stream);
+
+int basd_expand_ranks(const int* ranks, int E, int L, int* dims, void* stream);
+int basd_mask_block(const float* src, float* dst, int D, const int* dims, int batch, void* stream);
+
+/* d[i,l] = sum_m sw_m acos(min(sig_m,1-eps))^2 / sum_m sw_m   (layer_selector.py:100-105) */
+int basd_angle_distance(const float* sig, const float* lam_c, const int* ranks, int D, int E, int L,
+                        float* dist, void* stream);
+
+/* weights = softmax(-d / softplus(log_temp))                  (layer_selector.py:67,107-108) */
+int basd_mix_weights(const float* dist, const float* log_temp, int E, int L, float* weights,
+                     float* temps, void* stream);
+int basd_mix_weights_bwd(const float* d_weights, const float* weights, const float* dist,
+                         const float* log_temp, int E, int L, float scale, float* d_dist,
+                         float* d_log_temp, void* stream);
+int basd_scale_rows_dsigma(float* Uxt, const float* sig, const float* lam_c, const int* ranks,
+                           const float* d_dist, int D, int E, int L, void* stream);
+int basd_omega_accumulate(const float* block, const float* lam_s, const int* ranks, int D, int E,
+                          int L, float* omega, void* stream);
+int basd_symmetrize_add(const float* in, int D, float* out, int batch, void* stream);
+
+/* ---- HBM-bound mixing (mix.cu) ------------------------------------------------------ */
+
+/* attention map (B,H,side,side) -> importance row (B, n_tok): CLS row mean over heads, or
+ * mean over (heads, queries) without CLS.                      (relational.py:22-27) */
+int basd_attn_rows(const void* attn, int dtype, int B, int H, int side, int has_cls, float* rows,
+                   void* stream);
+
+/* out[i] = resample_{n_src->n_dst}( sum_l weights[i,l] * teacher_l ), all i in one pass.
+ * teacher_layers: HOST array of L device pointers, each (B, n_src, D).
+ *                                                (layer_selector.py:110-111, combined.py:9-14) */
+int basd_mix_interp(const void* const* teacher_layers, int L, int E, const float* weights,
+                    int in_dtype, int B, int n_src, int n_dst, int D, void* out, int out_dtype,
+                    void* stream);
+
+/* mixed + resampled + normalised token importance.   (layer_selector.py:112, relational.py:29-34) */
+int basd_mix_rows(const float* rows, const float* weights, int E, int L, int B, int n_src,
+                  int n_dst, float* w_out, float* totals, void* stream);
+
+/* dL/dweights[i,l] = <Z_i, resample(teacher_l)> + gw_scale * <gw_i, resample(rows_l)>.
+ * partial: scratch of basd_weight_grad_slices() * L * E floats. */
+int basd_weight_grad_slices(void);
+int basd_weight_grad(const void* const* teacher_layers, int L, int E, const float* Z,
+                     const float* gw, const float* rows, int in_dtype, int B, int n_src, int n_dst,
+                     int D, float gw_scale, const float* gw_scale_dev, float* partial,
+                     float* d_weights, void* stream);
+
+/* ---- Procrustes glue (procrustes.cu) ------------------------------------------------ */
+
+/* out = sqrt(w) * (X - sum_n w_n X_n) per sample.                 (relational.py:36-43) */
+int basd_weighted_center(const void* X, int dtype, long stride_x, const float* W, long stride_w,
+                         int N, int D, float* out, long stride_o, int batch, void* stream);
+int basd_extract_diag(const float* K, int N, int ld, long stride, int batch, float* diag,
+                      void* stream);
+int basd_procrustes_rows_finish(float* rows2, float* Ut, int N, int ld, long stride, int batch,
+                                float rel_floor, float* sig, float* nuc, void* stream);
+int basd_procrustes_grad_prep(float* YA, float* YB, const float* FAt, const float* FBt, int N,
+                              int ld, long stride, int batch, const float* sig, const float* nuc,
+                              const float* ks, const float* kt, const float* w,
+                              const float* totals, float* f_out, float* gw, int with_grad,
+                              void* stream);
+/* geo_terms[i] = mean_b f[i,b], geo = mean_i geo_terms[i].  (relational.py:50, combined.py:76) */
+int basd_geo_reduce(const float* f, int E, int B, float* geo_terms, float* geo, void* stream);
+int basd_cast_out(const float* src, void* dst, int dtype, long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASD_B200_H */

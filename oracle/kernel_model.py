@@ -139,14 +139,15 @@ def interp_taps(n_src: int, n_dst: int):
 def mix_and_align(weights_row, teacher_stack, n_student):
     """Mixed + aligned teacher tokens for one student layer (kernel: mix_interp).
     fp32 arithmetic on the (exactly upcast) tokens -- layer_selector.py:110-111 then
-    combined.py:12 -- with ONE final rounding to the token dtype, which is how the
-    kernel stores its output (bf16 tokens -> bf16 aligned tokens)."""
+    combined.py:12.  The kernel stores bf16 only when the tokens are bf16 AND no resampling
+    happens; resampled tokens are rank-deficient and their Procrustes term is sensitive to
+    rounding noise (1.5e-3 on the loss, gradient cosine 0.97), so they stay fp32."""
     dt = teacher_stack.dtype
     mixed = (weights_row.view(-1, 1, 1, 1) * teacher_stack.float()).sum(dim=0)   # (B,N_t,D_t)
     n_t = mixed.shape[1]
     if n_t != n_student:
         lo, hi, frac = interp_taps(n_t, n_student)
-        mixed = mixed[:, lo] * (1 - frac).view(1, -1, 1) + mixed[:, hi] * frac.view(1, -1, 1)
+        return mixed[:, lo] * (1 - frac).view(1, -1, 1) + mixed[:, hi] * frac.view(1, -1, 1)
     return _round_like(mixed, dt)
 
 

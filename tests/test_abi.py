@@ -1,0 +1,61 @@
+"""The C-ABI library builds in-tree, loads, and exports every symbol include/basd_b200.h
+declares (no compute here: there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "basd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|long)\s+(basd_\w+)\s*\(", text)))
+
+
+def test_library_exports_header_symbols():
+    import __graft_entry__ as entry
+    entry.build()
+    from basd_b200 import _native as nat
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in basd_b200.h but not exported"
+
+
+def test_binding_table_matches_header():
+    from basd_b200 import _native as nat
+    declared = set(header_symbols())
+    bound = set(nat.exported_symbols())
+    assert bound <= declared, f"bound but undeclared: {bound - declared}"
+    assert declared - bound <= set(nat._OPTIONAL), f"declared but unbound: {declared - bound}"
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from basd_b200 import _native as nat
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", "/nonexistent/libbasd_b200.so")
+    try:
+        nat.load()
+    except nat.NativeLibraryMissing as e:
+        assert "no" in str(e) and "fallback" in str(e)
+    else:
+        raise AssertionError("loading a missing library must raise")
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    import types
+    from basd_b200.losses import BASDLoss
+    mod = BASDLoss(torch.nn.CrossEntropyLoss(), 192, 384, 12, 64,
+                   config=types.SimpleNamespace(num_extraction_points=4), teacher_has_cls_token=True)
+    st = {l: torch.randn(16, 64, 192) for l in mod.token_layers}
+    te = {l: torch.randn(16, 64, 384) for l in range(2)}
+    at = {l: torch.softmax(torch.randn(16, 2, 65, 65), -1) for l in range(2)}
+    try:
+        mod(torch.randn(16, 10), torch.zeros(16, dtype=torch.long), st, te, at)
+    except RuntimeError as e:
+        assert "CUDA" in str(e) or "CPU" in str(e)
+    else:
+        raise AssertionError("CPU tensors must not silently run")

@@ -1,0 +1,245 @@
+"""Per-kernel checks of the C-ABI entry points on a real GPU (fp64 torch as the yardstick)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _eng():
+    from basd_b200 import _engine as eng
+    return eng
+
+
+def _nat():
+    from basd_b200 import _native as nat
+    return nat
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_sgemm_all_layouts(ta, tb):
+    eng = _eng()
+    torch.manual_seed(0)
+    b, m, n, k = 3, 70, 45, 133
+    a = torch.randn(b, *( (k, m) if ta else (m, k)), device=DEV)
+    bb = torch.randn(b, *((n, k) if tb else (k, n)), device=DEV)
+    c = torch.randn(b, m, n, device=DEV)
+    c0 = c.clone()
+    alpha_dev = torch.tensor([0.5], device=DEV)
+    eng.sgemm(ta, tb, m, n, k, a, a.shape[2], a[0].numel(), bb, bb.shape[2], bb[0].numel(), c, n,
+              m * n, b, alpha=2.0, alpha_dev=alpha_dev, beta=0.25)
+    ao = a.transpose(1, 2) if ta else a
+    bo = bb.transpose(1, 2) if tb else bb
+    ref = (ao.double() @ bo.double()) * 1.0 + 0.25 * c0.double()
+    assert (c.double() - ref).abs().max() < 1e-4
+
+
+def test_sgemm_bf16_a_with_shift_and_shared_operand():
+    eng = _eng()
+    torch.manual_seed(1)
+    m, n, k = 200, 96, 96
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    shift = torch.randn(k, device=DEV)
+    w = torch.randn(k, n, device=DEV)
+    c = torch.zeros(m, n, device=DEV)
+    eng.sgemm(0, 0, m, n, k, a, k, 0, w, n, 0, c, n, 0, 1, a_shift=shift)
+    ref = (a.double() - shift.double()) @ w.double()
+    assert (c.double() - ref).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,d", [(1024, 192), (4 * 196, 384), (3001, 200)])
+def test_token_gram(dtype, rows, d):
+    eng = _eng()
+    torch.manual_seed(2)
+    x = (torch.randn(rows, d, device=DEV) + 0.3).to(dtype)
+    gram = torch.empty(d, d, device=DEV)
+    col = torch.empty(d, device=DEV)
+    eng.token_gram(x.view(1, rows, d), gram, col)
+    ref = x.double().T @ x.double()
+    assert (gram.double() - ref).abs().max() / ref.abs().max() < 2e-6
+    assert (col.double() - x.double().sum(0)).abs().max() < 1e-2 * max(1.0, float(x.double().sum(0).abs().max())) * 1e-3
+    assert (gram - gram.T).abs().max() == 0
+
+
+@pytest.mark.parametrize("n,rank", [(64, 64), (196, 195), (196, 48), (384, 384)])
+def test_pivoted_cholesky(n, rank):
+    eng = _eng()
+    torch.manual_seed(3)
+    batch = 5
+    a = torch.randn(batch, n, rank, device=DEV) * torch.logspace(0, -1.5, rank, device=DEV)
+    k = a @ a.transpose(1, 2)
+    k = 0.5 * (k + k.transpose(1, 2))
+    work = k.clone()
+    lt = torch.empty_like(k)
+    ranks = torch.zeros(batch, dtype=torch.int32, device=DEV)
+    eng.pivoted_cholesky(work, lt, 1e-6, rank_out=ranks)
+    rec = lt.transpose(1, 2) @ lt
+    err = (rec - k).abs().amax(dim=(1, 2)) / k.abs().amax(dim=(1, 2))
+    assert err.max() < 2e-5, err
+    assert ranks.max() <= rank and ranks.min() >= min(rank, n) - 3, ranks
+
+
+@pytest.mark.parametrize("n", [64, 131, 196, 384])
+def test_jacobi_rows_orthogonalises(n):
+    eng = _eng()
+    torch.manual_seed(4)
+    batch = 4
+    ld = (n + 3) // 4 * 4
+    g = torch.zeros(batch, n, ld, device=DEV)
+    g[:, :, :n] = torch.randn(batch, n, n, device=DEV) * torch.logspace(0, -2, n, device=DEV)
+    ref_sv = torch.linalg.svdvals(g[:, :, :n].double())
+    sweeps = torch.zeros(batch, dtype=torch.int32, device=DEV)
+    dims = torch.full((batch,), n, dtype=torch.int32, device=DEV)
+    from basd_b200._native import call, ptr, stream
+    call("basd_jacobi_rows", ptr(g), n, ld, ld, n * ld, batch, ptr(dims), 1e-6, 18, ptr(sweeps), stream())
+    rows = g[:, :, :n].double()
+    gram = rows @ rows.transpose(1, 2)
+    nrm = gram.diagonal(dim1=1, dim2=2).sqrt()
+    off = gram / (nrm.unsqueeze(1) * nrm.unsqueeze(2)).clamp(min=1e-30)
+    off = off - torch.diag_embed(off.diagonal(dim1=1, dim2=2))
+    assert off.abs().max() < 2e-5, (float(off.abs().max()), sweeps)
+    sv = nrm.sort(dim=1, descending=True).values
+    assert ((sv - ref_sv).abs().max(dim=1).values / ref_sv[:, 0]).max() < 5e-5
+    assert sweeps.max() < 18, sweeps
+
+
+@pytest.mark.parametrize("d", [192, 384])
+def test_sym_eig(d):
+    eng = _eng()
+    torch.manual_seed(5)
+    x = torch.randn(3, 4 * d, d, device=DEV) * torch.logspace(0, -2, d, device=DEV)
+    k = x.transpose(1, 2) @ x
+    k = 0.5 * (k + k.transpose(1, 2))
+    lam, vt = eng.sym_eig(k)
+    ref = torch.linalg.eigvalsh(k.double()).flip(1)
+    assert ((lam.double() - ref).abs().max(dim=1).values / ref[:, 0]).max() < 2e-6
+    eye = torch.eye(d, device=DEV)
+    assert (vt @ vt.transpose(1, 2) - eye).abs().max() < 5e-5
+    resid = (vt @ k - lam.unsqueeze(2) * vt).abs().max() / ref[:, 0].max()
+    assert resid < 5e-5
+
+
+def test_mp_rank_kernel_matches_rule():
+    nat = _nat()
+    from basd_b200._native import call, ptr, stream
+    from oracle import kernel_model as km
+    torch.manual_seed(6)
+    d, rows = 96, 1000
+    lam = (torch.rand(5, d, device=DEV) * torch.logspace(1, -2, d, device=DEV))
+    ranks = torch.zeros(5, dtype=torch.int32, device=DEV)
+    call("basd_mp_rank", ptr(lam), d, rows, d - 1, ptr(ranks), None, 5, stream())
+    for i in range(5):
+        want = km.mp_rank_from_spectrum(lam[i].cpu().sort(descending=True).values, rows, d - 1)
+        assert int(ranks[i]) == want
+
+
+@pytest.mark.parametrize("has_cls,dtype", [(True, torch.float32), (False, torch.float32), (True, torch.bfloat16)])
+def test_attn_rows(has_cls, dtype):
+    from basd_b200._native import call, ptr, stream, dtype_code
+    torch.manual_seed(7)
+    b, h, side = 5, 3, 50
+    attn = torch.softmax(torch.randn(b, h, side, side, device=DEV), -1).to(dtype)
+    n_tok = side - 1 if has_cls else side
+    rows = torch.empty(b, n_tok, device=DEV)
+    call("basd_attn_rows", ptr(attn), dtype_code(attn), b, h, side, int(has_cls), ptr(rows), stream())
+    a = attn.float()
+    ref = a[:, :, 0, 1:].mean(1) if has_cls else a.mean((1, 2))
+    assert (rows - ref).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("dtype,n_src,n_dst", [(torch.bfloat16, 196, 196), (torch.bfloat16, 49, 196),
+                                               (torch.float32, 64, 64), (torch.float32, 256, 196)])
+def test_mix_interp_and_weight_grad(dtype, n_src, n_dst):
+    from basd_b200._native import call, ptr, stream, dtype_code, load
+    from oracle import kernel_model as km
+    torch.manual_seed(8)
+    l, e, b, d = 5, 4, 3, 64
+    layers = [torch.randn(b, n_src, d, device=DEV).to(dtype) for _ in range(l)]
+    w = torch.softmax(torch.randn(e, l, device=DEV), 1)
+    out_dtype = torch.bfloat16 if (dtype == torch.bfloat16 and n_src == n_dst) else torch.float32
+    out = torch.empty(e, b, n_dst, d, dtype=out_dtype, device=DEV)
+    ptrs = (ctypes.c_void_p * l)(*[t.data_ptr() for t in layers])
+    call("basd_mix_interp", ptrs, l, e, ptr(w), dtype_code(layers[0]), b, n_src, n_dst, d, ptr(out),
+         dtype_code(out), stream())
+    stack = torch.stack(layers).cpu()
+    for i in range(e):
+        ref = km.mix_and_align(w[i].cpu(), stack, n_dst)
+        tol = 2e-2 if out_dtype == torch.bfloat16 else 1e-5
+        assert (out[i].float().cpu() - ref).abs().max() < tol
+    # weight gradient: <Z_i, resample(T_l)> + scale * <gw_i, resample(rows_l)>
+    z = torch.randn(e, b, n_dst, d, device=DEV)
+    gw = torch.randn(e, b, n_dst, device=DEV)
+    rows = torch.rand(l, b, n_src, device=DEV)
+    slices = load().basd_weight_grad_slices()
+    partial = torch.empty(slices * l * e, device=DEV)
+    dw = torch.empty(e, l, device=DEV)
+    sc = torch.tensor([0.7], device=DEV)
+    call("basd_weight_grad", ptrs, l, e, ptr(z), ptr(gw), ptr(rows), dtype_code(layers[0]), b, n_src,
+         n_dst, d, 0.5, ptr(sc), ptr(partial), ptr(dw), stream())
+    lo, hi, fr = km.interp_taps(n_src, n_dst)
+    lo, hi, fr = lo.to(DEV), hi.to(DEV), fr.to(DEV)
+    for j in range(l):
+        t = layers[j].double()
+        r = rows[j].double()
+        if n_src != n_dst:
+            t = t[:, lo] * (1 - fr.double()).view(1, -1, 1) + t[:, hi] * fr.double().view(1, -1, 1)
+            r = r[:, lo] * (1 - fr.double()) + r[:, hi] * fr.double()
+        for i in range(e):
+            ref = (z[i].double() * t).sum() + 0.35 * (gw[i].double() * r).sum()
+            assert abs(float(dw[i, j]) - float(ref)) < 1e-3 * (1 + abs(float(ref)))
+
+
+def test_mix_rows():
+    from basd_b200._native import call, ptr, stream
+    from oracle import kernel_model as km
+    torch.manual_seed(9)
+    l, e, b, n_src, n_dst = 4, 3, 5, 49, 196
+    rows = torch.rand(l, b, n_src, device=DEV)
+    w = torch.softmax(torch.randn(e, l, device=DEV), 1)
+    out = torch.empty(e, b, n_dst, device=DEV)
+    tot = torch.empty(e, b, device=DEV)
+    call("basd_mix_rows", ptr(rows), ptr(w), e, l, b, n_src, n_dst, ptr(out), ptr(tot), stream())
+    for i in range(e):
+        ref, t = km.mix_importance(w[i].cpu(), rows.cpu(), n_dst)
+        assert (out[i].cpu() - ref).abs().max() < 1e-6
+        assert (tot[i].cpu() - t[:, 0]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("n,d_s,d_t,rank_t", [(64, 192, 384, 64), (196, 384, 768, 196), (196, 384, 512, 40)])
+def test_procrustes_stage_value_and_gradients(n, d_s, d_t, rank_t):
+    """procrustes_forward/backward on one mixing layer against the model and autograd."""
+    eng = _eng()
+    from oracle import kernel_model as km, ref_port as rp
+    torch.manual_seed(10)
+    b = 3
+    s = torch.randn(b, n, d_s) * torch.logspace(0, -1.5, d_s) + 0.2
+    base = torch.randn(b, rank_t, d_t) * torch.logspace(0, -1.5, d_t)
+    t = base if rank_t == n else torch.nn.functional.interpolate(
+        base.transpose(1, 2), size=n, mode="linear", align_corners=False).transpose(1, 2)
+    rows = torch.rand(1, b, n) + 0.1
+    stats = eng.Stats(None, None, None, None, rows.to(DEV))
+    w1 = torch.ones(1, 1, device=DEV)
+    sd, td = s.to(DEV), t.contiguous().to(DEV)
+    pro = eng.procrustes_forward([sd], [td], stats, w1, n, True)
+    go = torch.tensor(1.0, device=DEV)
+    grads, dw, z = eng.procrustes_backward([sd], [td], stats, pro, go, n, want_teacher_grad=True)
+    torch.cuda.synchronize()
+    w = rows[0] / rows[0].sum(1, keepdim=True)
+    for i in range(b):
+        f, gs, gt, gwn = km.procrustes_sample(s[i], t[i], w[i])
+        assert abs(float(pro.f[i]) - float(f)) / abs(float(f)) < 2e-4, (float(pro.f[i]), float(f))
+        from tests._cases import cosine
+        assert cosine(grads[0][i].cpu(), gs / b) > 0.9995
+        assert cosine(z[0, i].cpu(), gt / b) > 0.999
+    # and against the reference formulation by autograd (value)
+    sg = s.clone().requires_grad_(True)
+    fake_attn = torch.zeros(b, 1, n + 1, n + 1)
+    fake_attn[:, 0, 0, 1:] = rows[0]
+    ref = rp.procrustes_loss(sg, t, fake_attn, True)
+    ref.backward()
+    assert abs(float(pro.geo) - float(ref)) / abs(float(ref)) < 1e-3
+    assert cosine(grads[0].cpu(), sg.grad) > 0.999

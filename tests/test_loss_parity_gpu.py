@@ -1,0 +1,125 @@
+"""End-to-end parity of the CUDA loss (through the reference-shaped module API and the C ABI)
+with (a) golden outputs of the real reference and (b) the live CPU oracle on the same inputs.
+
+Tolerances are the ones BASELINE.json's north star states:
+  mixing weights <= 1e-4 abs, loss <= 1e-3 rel (fp32), gradient cosine >= 0.999,
+  MP ranks equal (or flagged as a tie when an eigenvalue sits within 1e-4 of the edge).
+"""
+import pytest
+import torch
+
+import basd_b200.synthetic as syn
+from tests import _cases as cs
+
+pytestmark = pytest.mark.gpu
+
+W_TOL, LOSS_TOL, COS_TOL = 1e-4, 1e-3, 0.999
+
+
+def _ranks_ok(got, ref, module):
+    if got == ref:
+        return True
+    st = module.layer_selector.last_state
+    lam, edges = st.lam_u.cpu(), st.edges.cpu()
+    for j, (a, b) in enumerate(zip(got, ref)):
+        if a != b:
+            gap = ((lam[j] - edges[j, 1]).abs() / edges[j, 1]).min()
+            if abs(a - b) > 1 or gap > 1e-4:
+                return False
+    print("MP-rank tie flagged:", got, ref)
+    return True
+
+
+@pytest.mark.parametrize("name", ["c1_b16_seed0", "c1_b16_seed1_temps", "c2_b4_seed0", "c3_b8_seed0"])
+def test_against_reference_golden(name):
+    gold = cs.golden(name)
+    work = cs.workload(gold["workload"], gold["batch"])
+    inputs = syn.make_inputs(work, seed=gold["seed"])
+    got = cs.run_cuda(work, inputs, gold["log_temperatures"])
+    print(name, "loss", float(got["loss"]), "golden", float(gold["loss"]), "ranks", got["ranks"])
+    ranks_equal = got["ranks"] == gold["ranks"].tolist()
+    assert _ranks_ok(got["ranks"], gold["ranks"].tolist(), got["module"])
+    if ranks_equal:
+        assert (got["weights"] - gold["weights"]).abs().max() < W_TOL
+    rel = abs(float(got["loss"]) - float(gold["loss"])) / abs(float(gold["loss"]))
+    assert rel < LOSS_TOL, rel
+    for layer in gold["token_layers"]:
+        g = got["grad_students"][layer]
+        ref = gold["grad_student"][layer]
+        idx = cs.probe_indices(g.numel(), 100 + layer)
+        c = cs.cosine(g.flatten()[idx], ref["probe"])
+        print("  layer", layer, "probe cosine", c, "norm", float(g.norm()), float(ref["norm"]))
+        assert c > COS_TOL
+    if work.teacher_layers > 1 and ranks_equal:
+        assert cs.cosine(got["grad_log_temps"], gold["grad_log_temperatures"]) > COS_TOL
+    idx = cs.probe_indices(got["grad_logits"].numel(), 5)
+    assert torch.allclose(got["grad_logits"].flatten()[idx], gold["grad_logits_probe"], atol=1e-6, rtol=1e-3)
+
+
+@pytest.mark.parametrize("key,batch,seed,temps", [
+    ("c1", 16, 5, [0.2, 0.6, 1.0, 1.4]),
+    ("c2", 8, 2, None),
+    ("c3", 8, 3, None),
+])
+def test_against_live_oracle(key, batch, seed, temps):
+    work = cs.workload(key, batch)
+    inputs = syn.make_inputs(work, seed=seed)
+    ref = cs.run_oracle(work, inputs, temps)
+    got = cs.run_cuda(work, inputs, temps)
+    print(key, "loss", float(got["loss"]), float(ref["loss"]), "geo", float(got["geo"]), float(ref["geo"]))
+    assert _ranks_ok(got["ranks"], ref["ranks"], got["module"])
+    ranks_equal = got["ranks"] == ref["ranks"]
+    if ranks_equal:
+        assert (got["dist"] - ref["dist"]).abs().max() < 1e-3
+        assert (got["weights"] - ref["weights"]).abs().max() < W_TOL
+    assert abs(float(got["geo"]) - float(ref["geo"])) / abs(float(ref["geo"])) < LOSS_TOL
+    assert abs(float(got["loss"]) - float(ref["loss"])) / abs(float(ref["loss"])) < LOSS_TOL
+    for layer in ref["layers"]:
+        c = cs.cosine(got["grad_students"][layer], ref["grad_students"][layer])
+        print("  layer", layer, "grad cosine", c)
+        assert c > COS_TOL
+    if work.teacher_layers > 1 and ranks_equal:
+        c = cs.cosine(got["grad_log_temps"], ref["grad_log_temps"])
+        print("  log_temperature grad cosine", c, got["grad_log_temps"], ref["grad_log_temps"])
+        assert c > COS_TOL
+    assert torch.allclose(got["grad_logits"], ref["grad_logits"], atol=1e-6, rtol=1e-3)
+
+
+def test_module_contract():
+    """state_dict keys, parameters and token_layers as the trainer reads them
+    (reference: trainer.py:74-76,84,142)."""
+    work = cs.workload("c1", 16)
+    mod = cs.build_cuda_module(work)
+    assert list(mod.state_dict().keys()) == ["layer_selector.log_temperatures",
+                                             "layer_selector.proj_s", "layer_selector.proj_t"]
+    assert [n for n, _ in mod.named_parameters()] == ["layer_selector.log_temperatures"]
+    assert mod.token_layers == [0, 4, 7, 11]
+    inputs = syn.make_inputs(work, seed=0)
+    logits, targets, st, te, at = [x if not isinstance(x, dict) else {k: v.cuda() for k, v in x.items()}
+                                   for x in inputs]
+    with torch.no_grad():
+        loss = mod(logits.cuda(), targets.cuda(), st, te, at)
+    assert loss.dim() == 0 and torch.isfinite(loss)
+    assert set(mod.layer_selector.subspace_ranks.keys()) == set(range(work.teacher_layers))
+
+
+def test_standalone_entry_points():
+    from basd_b200.losses import geometric_relational_loss, marchenko_pastur_rank, _align_token_count
+    from oracle import ref_port as rp
+    torch.manual_seed(0)
+    b, n, ds, dt = 4, 64, 96, 128
+    s = torch.randn(b, n, ds)
+    t = torch.randn(b, n, dt)
+    attn = torch.softmax(torch.randn(b, 2, n + 1, n + 1), -1)
+    sg = s.clone().requires_grad_(True)
+    ref = rp.procrustes_loss(sg, t, attn, True)
+    ref.backward()
+    sd = s.cuda().requires_grad_(True)
+    got = geometric_relational_loss(sd, t.cuda(), attn.cuda(), has_cls_token=True)
+    got.backward()
+    assert abs(float(got) - float(ref)) / abs(float(ref)) < LOSS_TOL
+    assert cs.cosine(sd.grad.cpu(), sg.grad) > COS_TOL
+    feats = torch.randn(2048, 96) * torch.logspace(0, -2, 96)
+    assert marchenko_pastur_rank(feats.cuda()) == rp.mp_rank(feats)
+    x = torch.randn(3, 49, 64)
+    assert (_align_token_count(x.cuda(), 196).cpu() - rp.align_tokens(x, 196)).abs().max() < 1e-5

@@ -1,0 +1,410 @@
+"""Host-side orchestration of the BASD kernels.
+
+Four device phases, each a fixed sequence of C-ABI calls enqueued on the current CUDA
+stream with no host synchronisation in between:
+
+  statistics  -> (all-reduce across data-parallel ranks) -> selector -> Procrustes forward
+  backward: Procrustes grads -> mixing-weight grads -> (all-reduce) -> selector backward
+
+torch is used for allocation, streams and collectives only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+
+from . import _native as nat
+from ._native import call, ptr, stream
+
+JACOBI_TOL = 1e-6
+JACOBI_SWEEPS = 18
+CHOL_TOL = 1e-6          # pivoted-Cholesky rank cut, relative to the largest diagonal
+GRAM_CHOL_TOL = 1e-7
+SV_FLOOR = 1e-6          # singular directions below this (relative) leave the polar factor
+
+
+def _f32(*shape, device):
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------- op wrappers
+def sgemm(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch=1, alpha=1.0,
+          alpha_dev=None, beta=0.0, a_shift=None):
+    call("basd_sgemm_batched", int(ta), int(tb), m, n, k, ptr(a), nat.dtype_code(a), lda, sa,
+         ptr(a_shift), ptr(b), ldb, sb, ptr(c), ldc, sc, batch, float(alpha), ptr(alpha_dev),
+         float(beta), stream())
+
+
+def token_gram(tokens: torch.Tensor, gram: torch.Tensor, colsum: torch.Tensor):
+    """gram (D,D) = X^T X, colsum (D) = X^T 1 for X = tokens.reshape(-1, D)."""
+    d = tokens.shape[-1]
+    rows = tokens.numel() // d
+    x = tokens if tokens.is_contiguous() else tokens.contiguous()
+    if x.dtype == torch.bfloat16 and nat.has("basd_token_gram_tc") and d % 64 == 0 and rows % 64 == 0:
+        nbytes = nat.load().basd_token_gram_tc_workspace_bytes(rows, d)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        call("basd_token_gram_tc", ptr(x), rows, d, ptr(gram), ptr(colsum), ptr(ws), stream())
+        return
+    nfl = nat.load().basd_token_gram_simt_workspace_floats(rows, d)
+    ws = _f32(nfl, device=x.device)
+    call("basd_token_gram_simt", ptr(x), nat.dtype_code(x), rows, d, ptr(gram), ptr(colsum),
+         ptr(ws), stream())
+
+
+def pivoted_cholesky(k, lt, rel_tol, dims=None, rank_out=None):
+    batch, n, _ = k.shape
+    call("basd_pivoted_cholesky", ptr(k), n, n, n * n, ptr(lt), n, n * n, batch, rel_tol,
+         ptr(rank_out), ptr(dims), stream())
+
+
+def jacobi_rows(g, dims=None, sweeps_out=None):
+    batch, n, m = g.shape
+    call("basd_jacobi_rows", ptr(g), n, m, m, n * m, batch, ptr(dims), JACOBI_TOL, JACOBI_SWEEPS,
+         ptr(sweeps_out), stream())
+
+
+def rows_normalize(g, out, vals, *, sort, square, rel_floor, dims=None):
+    batch, n, m = g.shape
+    call("basd_rows_normalize", ptr(g), n, m, m, n * m, ptr(out), m, n * m, ptr(vals), batch,
+         int(sort), int(square), rel_floor, ptr(dims), stream())
+
+
+def sym_eig(kmats: torch.Tensor):
+    """Batched symmetric PSD eigendecomposition: returns (lam (b,D) descending, Vt (b,D,D)
+    with eigenvectors as rows). Pivoted Cholesky -> row-Jacobi on the factor -> sort ->
+    Rayleigh-quotient refinement against the untouched matrix."""
+    batch, d, _ = kmats.shape
+    dev = kmats.device
+    work = kmats.clone()
+    lt = _f32(batch, d, d, device=dev)
+    pivoted_cholesky(work, lt, GRAM_CHOL_TOL)
+    jacobi_rows(lt)
+    vt = work                         # reuse: the Schur complement is dead
+    coarse = _f32(batch, d, device=dev)
+    rows_normalize(lt, vt, coarse, sort=True, square=True, rel_floor=0.0)
+    kv = lt                           # reuse
+    sgemm(0, 0, d, d, d, vt, d, d * d, kmats, d, d * d, kv, d, d * d, batch)
+    lam = _f32(batch, d, device=dev)
+    call("basd_rowdot", ptr(kv), d, d * d, ptr(vt), d, d * d, d, d, batch, ptr(lam), stream())
+    return lam, vt
+
+
+# ---------------------------------------------------------------------------- phases
+@dataclass
+class Stats:
+    gram_s: torch.Tensor      # (E, Ds, Ds) token-space
+    col_s: torch.Tensor       # (E, Ds)
+    gram_t: torch.Tensor      # (L, Dt, Dt)
+    col_t: torch.Tensor       # (L, Dt)
+    rows: torch.Tensor        # (L, B, Nt) attention importance rows (local shard)
+
+
+def _all_reduce(flat: torch.Tensor, group):
+    if group is not None or (dist.is_available() and dist.is_initialized()
+                             and dist.get_world_size() > 1):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+
+
+def statistics(students, teachers, attns, has_cls):
+    dev = students[0].device
+    e, l = len(students), len(teachers)
+    b, n_t, d_t = teachers[0].shape
+    d_s = students[0].shape[2]
+    # one flat buffer so the data-parallel exchange is a single all-reduce
+    sizes = [e * d_s * d_s, e * d_s, l * d_t * d_t, l * d_t]
+    flat = _f32(sum(sizes), device=dev)
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    gram_s = flat[offs[0]:offs[1]].view(e, d_s, d_s)
+    col_s = flat[offs[1]:offs[2]].view(e, d_s)
+    gram_t = flat[offs[2]:offs[3]].view(l, d_t, d_t)
+    col_t = flat[offs[3]:offs[4]].view(l, d_t)
+    for i, s in enumerate(students):
+        token_gram(s, gram_s[i], col_s[i])
+    for j, t in enumerate(teachers):
+        token_gram(t, gram_t[j], col_t[j])
+    rows = _f32(l, b, n_t, device=dev)
+    for j, a in enumerate(attns):
+        a = a if a.is_contiguous() else a.contiguous()
+        if a.dim() == 2:      # already an importance row (B, Nt): "next" row f1 of SURVEY §8
+            rows[j].copy_(a)
+            continue
+        _, h, side, _ = a.shape
+        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, int(has_cls), ptr(rows[j]),
+             stream())
+    return Stats(gram_s, col_s, gram_t, col_t, rows), flat
+
+
+def attention_only_stats(teachers, attns, has_cls):
+    """Importance rows only (stand-alone Procrustes use: no selector statistics needed)."""
+    dev = teachers[0].device
+    l = len(teachers)
+    b, n_t, _ = teachers[0].shape
+    rows = _f32(l, b, n_t, device=dev)
+    for j, a in enumerate(attns):
+        a = a if a.is_contiguous() else a.contiguous()
+        if a.dim() == 2:
+            rows[j].copy_(a)
+            continue
+        _, h, side, _ = a.shape
+        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, int(has_cls), ptr(rows[j]),
+             stream())
+    return Stats(None, None, None, None, rows)
+
+
+@dataclass
+class SelectorState:
+    ranks: torch.Tensor       # (L,) int32
+    edges: torch.Tensor       # (L,2) median, lambda_plus
+    lam_u: torch.Tensor       # (L, Ds) spectrum of the uncentred teacher second moment
+    lam_t: torch.Tensor       # (L, Ds) centred teacher eigenvalues
+    lam_s: torch.Tensor       # (E, Ds)
+    vt_s: torch.Tensor        # (E, Ds, Ds)
+    wfull: torch.Tensor       # (E*L, Ds, Ds)  V_s^T V_t
+    uxt: torch.Tensor         # (E*L, Ds, Ds)
+    vxt: torch.Tensor         # (E*L, Ds, Ds)
+    sig: torch.Tensor         # (E*L, Ds)
+    dist: torch.Tensor        # (E, L)
+    weights: torch.Tensor     # (E, L)
+    temps: torch.Tensor       # (E,)
+    mean_s: torch.Tensor      # (E, Ds) global token means
+    sweeps: dict = field(default_factory=dict)
+
+
+def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log_temps):
+    dev = proj_s.device
+    e, d_s, _ = stats.gram_s.shape
+    l, d_t, _ = stats.gram_t.shape
+    if rows_t < d_s or rows_s < d_s:
+        raise ValueError(
+            f"BASD kernels need at least D_s={d_s} token rows per layer (got {rows_s} student, "
+            f"{rows_t} teacher): the reference's M<D branch (layer_selector.py:14-15) is not built")
+    # --- rotate the token-space statistics by the fixed projections (exact in fp32)
+    tmp_t = _f32(l, d_s, d_t, device=dev)
+    sgemm(0, 0, d_s, d_t, d_t, proj_t, d_t, 0, stats.gram_t, d_t, d_t * d_t, tmp_t, d_t, d_s * d_t, l)
+    ghat_t = _f32(l, d_s, d_s, device=dev)
+    sgemm(0, 1, d_s, d_s, d_t, tmp_t, d_t, d_s * d_t, proj_t, d_t, 0, ghat_t, d_s, d_s * d_s, l)
+    chat_t = _f32(l, d_s, device=dev)
+    sgemm(0, 1, l, d_s, d_t, stats.col_t, d_t, 0, proj_t, d_t, 0, chat_t, d_s, 0, 1)
+    tmp_s = _f32(e, d_s, d_s, device=dev)
+    sgemm(0, 0, d_s, d_s, d_s, proj_s, d_s, 0, stats.gram_s, d_s, d_s * d_s, tmp_s, d_s, d_s * d_s, e)
+    ghat_s = _f32(e, d_s, d_s, device=dev)
+    sgemm(0, 1, d_s, d_s, d_s, tmp_s, d_s, d_s * d_s, proj_s, d_s, 0, ghat_s, d_s, d_s * d_s, e)
+    chat_s = _f32(e, d_s, device=dev)
+    sgemm(0, 1, e, d_s, d_s, stats.col_s, d_s, 0, proj_s, d_s, 0, chat_s, d_s, 0, 1)
+
+    # --- [uncentred teacher | centred teacher | centred student] eigenproblems in one batch
+    kall = _f32(2 * l + e, d_s, d_s, device=dev)
+    call("basd_center_gram", ptr(ghat_t), None, d_s, 0.0, ptr(kall[:l]), l, stream())
+    call("basd_center_gram", ptr(ghat_t), ptr(chat_t), d_s, 1.0 / rows_t, ptr(kall[l:2 * l]), l, stream())
+    call("basd_center_gram", ptr(ghat_s), ptr(chat_s), d_s, 1.0 / rows_s, ptr(kall[2 * l:]), e, stream())
+    lam, vt = sym_eig(kall)
+    lam_u, lam_t, lam_s = lam[:l], lam[l:2 * l], lam[2 * l:]
+    vt_t, vt_s = vt[l:2 * l], vt[2 * l:]
+
+    ranks = torch.empty(l, dtype=torch.int32, device=dev)
+    edges = _f32(l, 2, device=dev)
+    call("basd_mp_rank", ptr(lam_u), d_s, rows_t, d_s - 1, ptr(ranks), ptr(edges), l, stream())
+    dims = torch.empty(e * l, dtype=torch.int32, device=dev)
+    call("basd_expand_ranks", ptr(ranks), e, l, ptr(dims), stream())
+
+    # --- principal angles between span(V_s[:k]) and span(V_t[:k])
+    dd = d_s * d_s
+    wfull = _f32(e * l, d_s, d_s, device=dev)
+    gx = _f32(e * l, d_s, d_s, device=dev)
+    for i in range(e):
+        sgemm(0, 1, d_s, d_s, d_s, vt_s[i], d_s, 0, vt_t, d_s, dd, wfull[i * l:], d_s, dd, l)
+        sgemm(0, 1, d_s, d_s, d_s, vt_t, d_s, dd, vt_s[i], d_s, 0, gx[i * l:], d_s, dd, l)
+    call("basd_mask_block", ptr(gx), ptr(gx), d_s, ptr(dims), e * l, stream())
+    sweeps = torch.zeros(e * l, dtype=torch.int32, device=dev)
+    jacobi_rows(gx, dims=dims, sweeps_out=sweeps)
+    uxt = _f32(e * l, d_s, d_s, device=dev)
+    sig = _f32(e * l, d_s, device=dev)
+    rows_normalize(gx, uxt, sig, sort=True, square=False, rel_floor=SV_FLOOR, dims=dims)
+    vxt = gx                                             # reuse as rows2 = Uxt . X
+    sgemm(0, 0, d_s, d_s, d_s, uxt, d_s, dd, wfull, d_s, dd, vxt, d_s, dd, e * l)
+    rows_normalize(vxt, vxt, sig, sort=False, square=False, rel_floor=SV_FLOOR, dims=dims)
+
+    dist_el = _f32(e, l, device=dev)
+    call("basd_angle_distance", ptr(sig), ptr(lam_t), ptr(ranks), d_s, e, l, ptr(dist_el), stream())
+    weights = _f32(e, l, device=dev)
+    temps = _f32(e, device=dev)
+    call("basd_mix_weights", ptr(dist_el), ptr(log_temps), e, l, ptr(weights), ptr(temps), stream())
+    mean_s = stats.col_s / float(rows_s)
+    return SelectorState(ranks, edges, lam_u, lam_t, lam_s, vt_s, wfull, uxt, vxt, sig, dist_el,
+                         weights, temps, mean_s, {"kxk": sweeps})
+
+
+@dataclass
+class ProcrustesState:
+    a: torch.Tensor           # (E,B,N,Ds) fp32 weighted-centred student tokens
+    bm: torch.Tensor          # (E,B,N,Dt)
+    m_a: torch.Tensor | None  # (E*B,N,N)  2 sqrt(w) (I - Y_A)
+    m_b: torch.Tensor | None
+    gw: torch.Tensor | None   # (E,B,N)    d f / d w~
+    f: torch.Tensor           # (E*B,)
+    geo_terms: torch.Tensor   # (E,)
+    geo: torch.Tensor         # ()
+    aligned: torch.Tensor     # (E,B,N,Dt) mixed + aligned teacher tokens
+    w: torch.Tensor           # (E,B,N)
+    sweeps: torch.Tensor | None = None
+
+
+def procrustes_forward(students, teachers, stats: Stats, weights, n_student, with_grad: bool):
+    dev = students[0].device
+    e, l = len(students), len(teachers)
+    b, n_t, d_t = teachers[0].shape
+    d_s = students[0].shape[2]
+    n = n_student
+    tdt = teachers[0].dtype
+    out_dtype = torch.bfloat16 if (tdt == torch.bfloat16 and n_t == n) else torch.float32
+    aligned = torch.empty(e, b, n, d_t, dtype=out_dtype, device=dev)
+    tptrs = (nat.C.c_void_p * l)(*[t.data_ptr() for t in teachers])
+    call("basd_mix_interp", tptrs, l, e, ptr(weights), nat.dtype_code(teachers[0]), b, n_t, n, d_t,
+         ptr(aligned), nat.dtype_code(aligned), stream())
+    w = _f32(e, b, n, device=dev)
+    totals = _f32(e, b, device=dev)
+    call("basd_mix_rows", ptr(stats.rows), ptr(weights), e, l, b, n_t, n, ptr(w), ptr(totals), stream())
+
+    a = _f32(e, b, n, d_s, device=dev)
+    bm = _f32(e, b, n, d_t, device=dev)
+    for i, s in enumerate(students):
+        call("basd_weighted_center", ptr(s), nat.dtype_code(s), n * d_s, ptr(w[i]), n, n, d_s,
+             ptr(a[i]), n * d_s, b, stream())
+    call("basd_weighted_center", ptr(aligned), nat.dtype_code(aligned), n * d_t, ptr(w), n, n, d_t,
+         ptr(bm), n * d_t, e * b, stream())
+
+    p, nn = e * b, n * n
+    ks = _f32(p, n, n, device=dev)
+    kt = _f32(p, n, n, device=dev)
+    sgemm(0, 1, n, n, d_s, a, d_s, n * d_s, a, d_s, n * d_s, ks, n, nn, p)
+    sgemm(0, 1, n, n, d_t, bm, d_t, n * d_t, bm, d_t, n * d_t, kt, n, nn, p)
+    ks_diag = _f32(p, n, device=dev)
+    kt_diag = _f32(p, n, device=dev)
+    call("basd_extract_diag", ptr(ks), n, n, nn, p, ptr(ks_diag), stream())
+    call("basd_extract_diag", ptr(kt), n, n, nn, p, ptr(kt_diag), stream())
+    ls_t = _f32(p, n, n, device=dev)
+    lt_t = _f32(p, n, n, device=dev)
+    pivoted_cholesky(ks, ls_t, CHOL_TOL)
+    pivoted_cholesky(kt, lt_t, CHOL_TOL)
+    x0, g = ks, kt                                       # Schur complements are dead: reuse
+    sgemm(0, 1, n, n, n, ls_t, n, nn, lt_t, n, nn, x0, n, nn, p)      # X   = L_s^T L_t
+    sgemm(0, 1, n, n, n, lt_t, n, nn, ls_t, n, nn, g, n, nn, p)       # X^T
+    sweeps = torch.zeros(p, dtype=torch.int32, device=dev)
+    jacobi_rows(g, sweeps_out=sweeps)                    # rows -> sigma_j u_j^T
+    rows_normalize(g, g, None, sort=False, square=False, rel_floor=0.0)
+    ut = g
+    rows2 = _f32(p, n, n, device=dev)
+    sgemm(0, 0, n, n, n, ut, n, nn, x0, n, nn, rows2, n, nn, p)        # U^T X = S V^T
+    sig = _f32(p, n, device=dev)
+    nuc = _f32(p, device=dev)
+    call("basd_procrustes_rows_finish", ptr(rows2), ptr(ut), n, n, nn, p, SV_FLOOR, ptr(sig),
+         ptr(nuc), stream())
+    f = _f32(p, device=dev)
+    m_a = m_b = gw = None
+    if with_grad:
+        fa_t = x0                                        # reuse
+        fb_t = _f32(p, n, n, device=dev)
+        sgemm(0, 0, n, n, n, rows2, n, nn, lt_t, n, nn, fa_t, n, nn, p)   # (L_t v'_j)^T rows
+        sgemm(0, 0, n, n, n, ut, n, nn, ls_t, n, nn, fb_t, n, nn, p)      # (L_s u'_j)^T rows
+        m_a, m_b = ls_t, lt_t                            # reuse
+        sgemm(1, 0, n, n, n, fa_t, n, nn, fa_t, n, nn, m_a, n, nn, p)     # Y_A
+        sgemm(1, 0, n, n, n, fb_t, n, nn, fb_t, n, nn, m_b, n, nn, p)     # Y_B
+        gw = _f32(e, b, n, device=dev)
+        call("basd_procrustes_grad_prep", ptr(m_a), ptr(m_b), ptr(fa_t), ptr(fb_t), n, n, nn, p,
+             ptr(sig), ptr(nuc), ptr(ks_diag), ptr(kt_diag), ptr(w), ptr(totals), ptr(f), ptr(gw),
+             1, stream())
+    else:
+        call("basd_procrustes_grad_prep", None, None, None, None, n, n, nn, p, ptr(sig), ptr(nuc),
+             ptr(ks_diag), ptr(kt_diag), ptr(w), ptr(totals), ptr(f), None, 0, stream())
+    geo_terms = _f32(e, device=dev)
+    geo = _f32((), device=dev)
+    call("basd_geo_reduce", ptr(f), e, b, ptr(geo_terms), ptr(geo), stream())
+    return ProcrustesState(a, bm, m_a, m_b, gw, f, geo_terms, geo, aligned, w, sweeps)
+
+
+def procrustes_backward(students, teachers, stats: Stats, pro: ProcrustesState,
+                        grad_out: torch.Tensor, n_student: int, want_teacher_grad: bool = False):
+    """Returns (direct dL/dS_i list in the students' dtype, dL/dweights (E,L) for the local
+    shard, optional dL/d(aligned teacher tokens))."""
+    dev = students[0].device
+    e, l = len(students), len(teachers)
+    b, n_t, d_t = teachers[0].shape
+    d_s = students[0].shape[2]
+    n = n_student
+    p, nn = e * b, n * n
+    go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+    scale = 1.0 / (e * b)                                # d geo / d f_{i,b}
+    grad_s = _f32(e, b, n, d_s, device=dev)
+    sgemm(0, 0, n, d_s, n, pro.m_a, n, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
+          alpha=scale, alpha_dev=go)
+    z = _f32(e, b, n, d_t, device=dev)
+    sgemm(0, 0, n, d_t, n, pro.m_b, n, nn, pro.bm, d_t, n * d_t, z, d_t, n * d_t, p,
+          alpha=scale, alpha_dev=go)
+    # mixing-weight gradients: one pass over the teacher stack
+    slices = nat.load().basd_weight_grad_slices()
+    partial = _f32(slices * l * e, device=dev)
+    d_weights = _f32(e, l, device=dev)
+    tptrs = (nat.C.c_void_p * l)(*[t.data_ptr() for t in teachers])
+    call("basd_weight_grad", tptrs, l, e, ptr(z), ptr(pro.gw), ptr(stats.rows),
+         nat.dtype_code(teachers[0]), b, n_t, n, d_t, scale, ptr(go), ptr(partial), ptr(d_weights),
+         stream())
+    outs = [_cast_like(grad_s[i], s) for i, s in enumerate(students)]
+    return outs, d_weights, (z if want_teacher_grad else None)
+
+
+def _cast_like(src32: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    if like.dtype == torch.float32:
+        return src32.view(like.shape)
+    out = torch.empty(like.shape, dtype=like.dtype, device=like.device)
+    call("basd_cast_out", ptr(src32), ptr(out), nat.dtype_code(out), out.numel(), stream())
+    return out
+
+
+def selector_backward(students, sel: SelectorState, proj_s, log_temps, d_weights: torch.Tensor,
+                      group, world: int):
+    """d_weights (E,L): dL/dweights summed over this rank's samples. Returns
+    (list of dL/dS_i through the selector, dL/dlog_temps). Closed form of the SVD/eigh
+    backward: only cross-block terms survive."""
+    dev = students[0].device
+    e, l = sel.weights.shape
+    b, n, d_s = students[0].shape
+    d_weights = d_weights.detach().to(torch.float32).contiguous()
+    if world > 1:
+        d_weights = d_weights.clone()
+        _all_reduce(d_weights, group)
+    d_dist = _f32(e, l, device=dev)
+    d_logt = _f32(e, device=dev)
+    call("basd_mix_weights_bwd", ptr(d_weights), ptr(sel.weights), ptr(sel.dist), ptr(log_temps), e,
+         l, 1.0 / world, ptr(d_dist), ptr(d_logt), stream())
+    dd = d_s * d_s
+    uxt = sel.uxt.clone()
+    call("basd_scale_rows_dsigma", ptr(uxt), ptr(sel.sig), ptr(sel.lam_t), ptr(sel.ranks),
+         ptr(d_dist), d_s, e, l, stream())
+    t1 = _f32(e * l, d_s, d_s, device=dev)
+    sgemm(0, 1, d_s, d_s, d_s, sel.wfull, d_s, dd, sel.vxt, d_s, dd, t1, d_s, dd, e * l)
+    blk = _f32(e * l, d_s, d_s, device=dev)
+    sgemm(0, 0, d_s, d_s, d_s, t1, d_s, dd, uxt, d_s, dd, blk, d_s, dd, e * l)
+    omega = _f32(e, d_s, d_s, device=dev)
+    call("basd_omega_accumulate", ptr(blk), ptr(sel.lam_s), ptr(sel.ranks), d_s, e, l, ptr(omega),
+         stream())
+    t2 = _f32(e, d_s, d_s, device=dev)
+    sgemm(1, 0, d_s, d_s, d_s, sel.vt_s, d_s, dd, omega, d_s, dd, t2, d_s, dd, e)     # V Omega
+    d_gram = _f32(e, d_s, d_s, device=dev)
+    sgemm(0, 0, d_s, d_s, d_s, t2, d_s, dd, sel.vt_s, d_s, dd, d_gram, d_s, dd, e)    # . V^T
+    w_sym = t2
+    call("basd_symmetrize_add", ptr(d_gram), d_s, ptr(w_sym), e, stream())
+    t3 = d_gram
+    sgemm(1, 0, d_s, d_s, d_s, proj_s, d_s, 0, w_sym, d_s, dd, t3, d_s, dd, e)        # P^T W
+    w_prime = omega
+    sgemm(0, 0, d_s, d_s, d_s, t3, d_s, dd, proj_s, d_s, 0, w_prime, d_s, dd, e)      # . P
+    outs = []
+    for i, s in enumerate(students):
+        g32 = _f32(b, n, d_s, device=dev)
+        sgemm(0, 0, b * n, d_s, d_s, s, d_s, 0, w_prime[i], d_s, 0, g32, d_s, 0, 1,
+              a_shift=sel.mean_s[i])
+        outs.append(_cast_like(g32, s))
+    return outs, d_logt

@@ -1,0 +1,383 @@
+// Batched small-matrix factorisation kernels (one CTA per problem, matrix resident in
+// shared memory when it fits, otherwise L2-resident global memory):
+//
+//   basd_pivoted_cholesky : K (PSD, n x n) -> rows of L^T, diagonal pivoting, rank-revealing
+//   basd_jacobi_rows      : one-sided (Hestenes) Jacobi that orthogonalises the ROWS of a
+//                           row-major matrix with warp-shuffle dot products and in-register
+//                           plane rotations, round-robin (circle) pair schedule.
+//   basd_rows_normalize   : row norms, optional descending sort, unit rows.
+//   basd_rowdot           : per-row dot product of two matrices (Rayleigh refinement).
+//
+// These serve: the symmetric eigenproblems of the projected Gram matrices
+// (reference: torch.linalg.eigvalsh / svd at layer_selector.py:16,36,92 -> Cholesky factor +
+// row-Jacobi = Veselic-Hari), the k x k principal-angle SVDs (layer_selector.py:99) and the
+// per-sample Procrustes SVD (relational.py:48, reduced to N x N).
+#include "common.cuh"
+
+namespace basd {
+
+// ------------------------------------------------------------------ pivoted Cholesky
+// K is overwritten (used as the Schur complement). Output LT (n x n, row j = j-th column of
+// L, rows >= rank are zero) so that K ~= LT^T LT.  `dims` (optional) gives the active
+// leading dimension per problem; everything outside it is written as zero.
+__global__ void pivoted_cholesky_kernel(float* __restrict__ Kbase, int n, int ld, long strideK,
+                                        float* __restrict__ LTbase, int ldl, long strideL,
+                                        float rel_tol, int* __restrict__ rank_out,
+                                        const int* __restrict__ dims, int use_smem) {
+  extern __shared__ __align__(16) float smem[];
+  const int prob = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  float* Kg = Kbase + (long)prob * strideK;
+  float* LT = LTbase + (long)prob * strideL;
+  const int nn = dims ? min(dims[prob], n) : n;
+  float* colv = smem;                // n
+  float* diag = colv + n;            // n
+  float* red = diag + n;             // 64
+  int* redi = reinterpret_cast<int*>(red + 64);  // 64
+  float* As = red + 128;             // n*n when staged
+  float* A = use_smem ? As : Kg;
+  const int lda = use_smem ? nn : ld;
+  if (use_smem)
+    for (int e = tid; e < nn * nn; e += T) As[e] = Kg[(long)(e / nn) * ld + (e % nn)];
+  __syncthreads();
+  float dmax = 0.f;
+  for (int i = tid; i < nn; i += T) {
+    const float d = A[(long)i * lda + i];
+    diag[i] = d;
+    dmax = fmaxf(dmax, d);
+  }
+  dmax = block_max(dmax, red);
+  const float floor_v = rel_tol * dmax;
+  __syncthreads();
+  int rank = 0;
+  for (int j = 0; j < nn; ++j) {
+    // ---- block argmax of the remaining diagonal (eliminated entries hold -1)
+    float best = -1.f;
+    int arg = 0;
+    for (int i = tid; i < nn; i += T) {
+      const float d = diag[i];
+      if (d > best) { best = d; arg = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = arg; }
+    __syncthreads();
+    const int nw = (T + 31) >> 5;
+    best = red[0];
+    arg = redi[0];
+    for (int w = 1; w < nw; ++w)
+      if (red[w] > best || (red[w] == best && redi[w] < arg)) { best = red[w]; arg = redi[w]; }
+    if (!(best > floor_v) || !(best > 0.f)) break;   // uniform across the block
+    const float rs = rsqrtf(best);
+    const int p = arg;
+    for (int i = tid; i < nn; i += T) {
+      float c = (diag[i] < 0.f) ? 0.f : A[(long)p * lda + i] * rs;
+      if (i == p) c = best * rs;
+      colv[i] = c;
+      LT[(long)j * ldl + i] = c;
+    }
+    __syncthreads();
+    for (int e = tid; e < nn * nn; e += T) {
+      const int i = e / nn, k = e - i * nn;
+      const float ci = colv[i], ck = colv[k];
+      if (ci != 0.f && ck != 0.f) A[(long)i * lda + k] -= ci * ck;
+    }
+    for (int i = tid; i < nn; i += T) {
+      if (i == p) diag[i] = -1.f;
+      else if (diag[i] >= 0.f) diag[i] = fmaxf(diag[i] - colv[i] * colv[i], 0.f);
+    }
+    __syncthreads();
+    rank = j + 1;
+  }
+  __syncthreads();
+  // zero the rest: rows >= rank, and (for dims) columns >= nn of every row
+  for (int e = tid; e < n * n; e += T) {
+    const int r = e / n, c = e - r * n;
+    if (r >= rank || c >= nn) LT[(long)r * ldl + c] = 0.f;
+  }
+  if (rank_out && tid == 0) rank_out[prob] = rank;
+}
+
+// ------------------------------------------------------------------ one-sided Jacobi on rows
+template <int NV>
+__global__ void __launch_bounds__((NV >= 3 ? 512 : 1024), 1)
+jacobi_rows_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                   const int* __restrict__ dims, float tol, int max_sweeps, int use_smem,
+                   int* __restrict__ sweeps_out) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int rot_count;
+  const int prob = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  float* Gg = Gbase + (long)prob * stride;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
+  const int mv = (mm + 3) >> 2;            // float4 per row
+  float* G = Gg;
+  int ldw = ld;
+  if (use_smem) {
+    ldw = mv * 4;
+    G = smem;
+    for (int e = tid; e < nn * mv; e += T) {
+      const int r = e / mv, c4 = (e - r * mv) * 4;
+      float4 v = *reinterpret_cast<const float4*>(Gg + (long)r * ld + c4);
+      if (c4 + 1 >= mm) v.y = 0.f;
+      if (c4 + 2 >= mm) v.z = 0.f;
+      if (c4 + 3 >= mm) v.w = 0.f;
+      *reinterpret_cast<float4*>(G + (long)r * ldw + c4) = v;
+    }
+  }
+  __syncthreads();
+  const int ne = nn + (nn & 1);
+  const int ring = ne - 1;
+  int sweep = 0;
+  for (; sweep < max_sweeps && nn >= 2; ++sweep) {
+    if (tid == 0) rot_count = 0;
+    __syncthreads();
+    for (int step = 0; step < ring; ++step) {
+      for (int pair = warp; pair < (ne >> 1); pair += nwarps) {
+        int p, q;
+        if (pair == 0) { p = ne - 1; q = step; }
+        else { p = (step + pair) % ring; q = (step - pair + ring) % ring; }
+        if (p >= nn || q >= nn) continue;   // bye (odd n)
+        float4* rp = reinterpret_cast<float4*>(G + (long)p * ldw);
+        float4* rq = reinterpret_cast<float4*>(G + (long)q * ldw);
+        float4 x[NV], y[NV];
+        float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int idx = lane + 32 * v;
+          if (idx < mv) {
+            x[v] = rp[idx];
+            y[v] = rq[idx];
+            if (!use_smem) {   // global rows may carry junk past mm only in the last quad
+              const int c4 = idx * 4;
+              if (c4 + 1 >= mm) { x[v].y = 0.f; y[v].y = 0.f; }
+              if (c4 + 2 >= mm) { x[v].z = 0.f; y[v].z = 0.f; }
+              if (c4 + 3 >= mm) { x[v].w = 0.f; y[v].w = 0.f; }
+            }
+          } else {
+            x[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            y[v] = x[v];
+          }
+          al = fmaf(x[v].x, x[v].x, al); al = fmaf(x[v].y, x[v].y, al);
+          al = fmaf(x[v].z, x[v].z, al); al = fmaf(x[v].w, x[v].w, al);
+          be = fmaf(y[v].x, y[v].x, be); be = fmaf(y[v].y, y[v].y, be);
+          be = fmaf(y[v].z, y[v].z, be); be = fmaf(y[v].w, y[v].w, be);
+          ga = fmaf(x[v].x, y[v].x, ga); ga = fmaf(x[v].y, y[v].y, ga);
+          ga = fmaf(x[v].z, y[v].z, ga); ga = fmaf(x[v].w, y[v].w, ga);
+        }
+        al = warp_sum(al);
+        be = warp_sum(be);
+        ga = warp_sum(ga);
+        const float lim = tol * sqrtf(al) * sqrtf(be);
+        if (!(fabsf(ga) > lim) || !(lim > 0.f)) continue;   // warp-uniform
+        const float zeta = (be - al) / (2.f * ga);
+        float t;
+        if (fabsf(zeta) > 1e8f) t = 0.5f / zeta;
+        else t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+        const float c = rsqrtf(fmaf(t, t, 1.f)), s = c * t;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int idx = lane + 32 * v;
+          if (idx < mv) {
+            float4 a = x[v], b = y[v], na, nb;
+            na.x = c * a.x - s * b.x; nb.x = s * a.x + c * b.x;
+            na.y = c * a.y - s * b.y; nb.y = s * a.y + c * b.y;
+            na.z = c * a.z - s * b.z; nb.z = s * a.z + c * b.z;
+            na.w = c * a.w - s * b.w; nb.w = s * a.w + c * b.w;
+            rp[idx] = na;
+            rq[idx] = nb;
+          }
+        }
+        if (lane == 0) atomicAdd(&rot_count, 1);
+      }
+      __syncthreads();
+    }
+    const int done = (rot_count == 0);
+    __syncthreads();
+    if (done) { ++sweep; break; }
+  }
+  if (use_smem) {
+    for (int e = tid; e < nn * mv; e += T) {
+      const int r = e / mv, c4 = (e - r * mv) * 4;
+      *reinterpret_cast<float4*>(Gg + (long)r * ld + c4) =
+          *reinterpret_cast<const float4*>(G + (long)r * ldw + c4);
+    }
+  }
+  if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
+}
+
+// ------------------------------------------------------------------ normalise (+ sort) rows
+// in:  G (n x m) whose rows are s_j * v_j^T ; out: Vt rows = v_j^T (zero if s_j <= floor),
+// vals[j] = s_j (square=0) or s_j^2 (square=1); sorted descending when sort != 0.
+// In-place (out == in) is allowed only when sort == 0.
+__global__ void rows_normalize_kernel(const float* __restrict__ Gbase, int n, int m, int ld,
+                                      long stride, float* __restrict__ Vbase, int ldv,
+                                      long strideV, float* __restrict__ vals, int sort, int square,
+                                      float rel_floor, const int* __restrict__ dims) {
+  extern __shared__ float sm[];
+  float* nrm = sm;                                // n
+  int* pos = reinterpret_cast<int*>(sm + n);      // n
+  float* red = sm + 2 * n;                        // 32
+  const int prob = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const float* G = Gbase + (long)prob * stride;
+  float* V = Vbase + (long)prob * strideV;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
+  for (int r = warp; r < nn; r += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < mm; c += 32) { const float v = G[(long)r * ld + c]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) nrm[r] = sqrtf(s);
+  }
+  __syncthreads();
+  float mx = 0.f;
+  for (int r = tid; r < nn; r += T) mx = fmaxf(mx, nrm[r]);
+  mx = block_max(mx, red);
+  const float floor_v = rel_floor * mx;
+  for (int r = tid; r < nn; r += T) {
+    int rank = r;
+    if (sort) {
+      rank = 0;
+      const float mine = nrm[r];
+      for (int j = 0; j < nn; ++j) {
+        const float o = nrm[j];
+        rank += (o > mine) || (o == mine && j < r);
+      }
+    }
+    pos[r] = rank;
+  }
+  __syncthreads();
+  for (int r = warp; r < nn; r += nwarps) {
+    const float s = nrm[r];
+    const bool keep = (s > floor_v) && (s > 0.f);
+    const float inv = keep ? 1.f / s : 0.f;
+    const int dst = pos[r];
+    for (int c = lane; c < m; c += 32)
+      V[(long)dst * ldv + c] = (c < mm) ? G[(long)r * ld + c] * inv : 0.f;
+    if (lane == 0 && vals) vals[(long)prob * n + dst] = square ? s * s : s;
+  }
+  // rows beyond the active dimension: zero
+  for (int r = nn + warp; r < n; r += nwarps) {
+    for (int c = lane; c < m; c += 32) V[(long)r * ldv + c] = 0.f;
+    if (lane == 0 && vals) vals[(long)prob * n + r] = 0.f;
+  }
+}
+
+// out[prob*n + r] = <A[r,:], B[r,:]>
+__global__ void rowdot_kernel(const float* __restrict__ A, int lda, long sA,
+                              const float* __restrict__ B, int ldb, long sB, int n, int m,
+                              float* __restrict__ out) {
+  const int prob = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float* a = A + (long)prob * sA + (long)r * lda;
+  const float* b = B + (long)prob * sB + (long)r * ldb;
+  float s = 0.f;
+  for (int c = lane; c < m; c += 32) s = fmaf(a[c], b[c], s);
+  s = warp_sum(s);
+  if (lane == 0) out[(long)prob * n + r] = s;
+}
+
+static int smem_limit() {
+  static int lim = -1;
+  if (lim < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  return lim;
+}
+
+template <int NV>
+static int launch_jacobi(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                         float tol, int max_sweeps, int* sweeps_out, cudaStream_t st) {
+  const size_t need = (size_t)n * (((size_t)m + 3) / 4 * 4) * sizeof(float);
+  const int use_smem = need + 1024 <= (size_t)smem_limit();
+  const size_t dyn = use_smem ? need : 0;
+  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_kernel<NV>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int pairs = (n + 1) / 2;
+  int threads = pairs * 32;
+  const int cap = NV >= 3 ? 512 : 1024;
+  if (threads > cap) threads = cap;
+  if (threads < 64) threads = 64;
+  jacobi_rows_kernel<NV><<<batch, threads, dyn, st>>>(G, n, m, ld, stride, dims, tol, max_sweeps,
+                                                      use_smem, sweeps_out);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace basd
+
+extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, float* LT, int ldl,
+                                     long stride_l, int batch, float rel_tol, int* rank_out,
+                                     const int* dims, void* stream) {
+  using namespace basd;
+  if (batch <= 0 || n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t base = (size_t)(2 * n + 128) * sizeof(float);
+  const size_t staged = base + (size_t)n * n * sizeof(float);
+  const int use_smem = staged + 1024 <= (size_t)smem_limit();
+  const size_t dyn = use_smem ? staged : base;
+  BASD_CUDA(cudaFuncSetAttribute(pivoted_cholesky_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int threads = n >= 128 ? 1024 : 256;
+  pivoted_cholesky_kernel<<<batch, threads, dyn, st>>>(K, n, ld, stride_k, LT, ldl, stride_l,
+                                                       rel_tol, rank_out, dims, use_smem);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+// Orthogonalises the rows of each (n x m) row-major matrix in place. ld % 4 == 0 and
+// 16-byte aligned bases are required (128-bit row accesses).
+extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int batch,
+                                const int* dims, float tol, int max_sweeps, int* sweeps_out,
+                                void* stream) {
+  using namespace basd;
+  if (batch <= 0 || n <= 0) return 0;
+  if ((ld & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(G) & 15)) return -3;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int quads = (m + 3) / 4;
+  const int nv = (quads + 31) / 32;
+  switch (nv) {
+    case 1: return launch_jacobi<1>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+    case 2: return launch_jacobi<2>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+    case 3: return launch_jacobi<3>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+    case 4: return launch_jacobi<4>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+    case 5: case 6:
+      return launch_jacobi<6>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+    case 7: case 8:
+      return launch_jacobi<8>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+    default: return -4;  // m > 1024 unsupported
+  }
+}
+
+extern "C" int basd_rows_normalize(const float* G, int n, int m, int ld, long stride, float* V,
+                                   int ldv, long stride_v, float* vals, int batch, int sort,
+                                   int square, float rel_floor, const int* dims, void* stream) {
+  using namespace basd;
+  if (batch <= 0 || n <= 0) return 0;
+  if (sort && G == V) return -5;
+  const size_t dyn = (size_t)(2 * n + 32) * sizeof(float);
+  rows_normalize_kernel<<<batch, 512, dyn, (cudaStream_t)stream>>>(
+      G, n, m, ld, stride, V, ldv, stride_v, vals, sort, square, rel_floor, dims);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_rowdot(const float* A, int lda, long stride_a, const float* B, int ldb,
+                           long stride_b, int n, int m, int batch, float* out, void* stream) {
+  using namespace basd;
+  if (batch <= 0 || n <= 0) return 0;
+  dim3 grid((n + 7) / 8, batch);
+  rowdot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, stride_a, B, ldb, stride_b, n, m,
+                                                        out);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,331 @@
+// HBM-bound kernels of the layer mixing (reference: layer_selector.py:110-112,
+// combined.py:9-14, relational.py:22-34 and the autograd of those lines).
+//
+//  basd_attn_rows     : attention map -> per-token importance row (CLS row / query mean),
+//                       reduced BEFORE mixing (mixing is linear) so the full
+//                       (L,B,H,N+1,N+1) stack is never materialised.
+//  basd_mix_interp    : all E mixed+aligned teacher tensors in ONE pass over the teacher
+//                       stack, 128-bit loads, 1-D linear resampling fused in.
+//  basd_mix_rows      : mixed, resampled, normalised importance weights.
+//  basd_weight_grad   : dL/d(mixing weights): inner products of the upstream token gradient
+//                       with every teacher layer, one pass over the stack.
+#include "common.cuh"
+
+namespace basd {
+
+constexpr int MAX_E = 8;
+constexpr int MAX_L = 64;
+
+struct LayerPtrs { const void* p[MAX_L]; };
+
+// 1-D linear taps, align_corners=False (ATen upsample_linear1d):
+//   src = max((i + .5) * n_src/n_dst - .5, 0); lo = floor(src); hi = min(lo+1, n_src-1)
+__device__ __forceinline__ void taps(int i, int n_src, int n_dst, int& lo, int& hi, float& f) {
+  if (n_src == n_dst) { lo = hi = i; f = 0.f; return; }
+  float src = (i + 0.5f) * ((float)n_src / (float)n_dst) - 0.5f;
+  src = fmaxf(src, 0.f);
+  lo = min((int)src, n_src - 1);
+  hi = min(lo + 1, n_src - 1);
+  f = src - (float)lo;
+}
+
+template <typename T>
+__global__ void attn_rows_kernel(const T* __restrict__ attn, int H, int side, int has_cls,
+                                 int n_tok, float* __restrict__ rows) {
+  const int b = blockIdx.x;
+  const T* base = attn + (long)b * H * side * side;
+  for (int n = threadIdx.x; n < n_tok; n += blockDim.x) {
+    float s = 0.f;
+    if (has_cls) {
+      for (int h = 0; h < H; ++h) s += to_f32<T>(base[(long)h * side * side + 1 + n]);
+      s /= (float)H;
+    } else {
+      for (int h = 0; h < H; ++h)
+        for (int q = 0; q < side; ++q) s += to_f32<T>(base[((long)h * side + q) * side + n]);
+      s /= (float)(H * side);
+    }
+    rows[(long)b * n_tok + n] = s;
+  }
+}
+
+// One thread per (b, n_dst, 8-wide column group). VEC = 8 elements.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+mix_interp_kernel(LayerPtrs layers, int L, int E, const float* __restrict__ weights, int B,
+                  int n_src, int n_dst, int D, TOut* __restrict__ out) {
+  __shared__ float w[MAX_E * MAX_L];
+  for (int i = threadIdx.x; i < E * L; i += blockDim.x) w[i] = weights[i];
+  __syncthreads();
+  const int groups = D >> 3;
+  const long total = (long)B * n_dst * groups;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % groups;
+  const long tok = idx / groups;
+  const int n = tok % n_dst;
+  const int b = tok / n_dst;
+  int lo, hi;
+  float f;
+  taps(n, n_src, n_dst, lo, hi, f);
+  float acc[MAX_E][8];
+#pragma unroll
+  for (int i = 0; i < MAX_E; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+  const long off_lo = ((long)b * n_src + lo) * D + g * 8;
+  const long off_hi = ((long)b * n_src + hi) * D + g * 8;
+  for (int l = 0; l < L; ++l) {
+    const TIn* src = reinterpret_cast<const TIn*>(layers.p[l]);
+    float v[8];
+    if (sizeof(TIn) == 2) {
+      load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_lo, v);
+      if (f != 0.f) {
+        float u[8];
+        load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_hi, u);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(f, u[c] - v[c], v[c]);
+      }
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off_lo);
+      const float4 a = __ldg(p), bq = __ldg(p + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+      if (f != 0.f) {
+        const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off_hi);
+        const float4 c0 = __ldg(q), c1 = __ldg(q + 1);
+        const float u[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(f, u[c] - v[c], v[c]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_E; ++i) {
+      if (i < E) {
+        const float wi = w[i * L + l];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(wi, v[c], acc[i][c]);
+      }
+    }
+  }
+  const long slab = (long)B * n_dst * D;
+  const long o = ((long)b * n_dst + n) * D + g * 8;
+#pragma unroll
+  for (int i = 0; i < MAX_E; ++i) {
+    if (i < E) {
+      TOut* dst = out + (long)i * slab + o;
+      if (sizeof(TOut) == 2) {
+        uint4 pk;
+        uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(acc[i][2 * c], acc[i][2 * c + 1]);
+          pw[c] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(dst) = pk;
+      } else {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        d4[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        d4[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+  }
+}
+
+// rows: (L, B, n_src) fp32. out w: (E, B, n_dst) normalised, totals: (E, B).
+__global__ void mix_rows_kernel(const float* __restrict__ rows, const float* __restrict__ weights,
+                                int L, int B, int n_src, int n_dst, float* __restrict__ w_out,
+                                float* __restrict__ totals) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, i = blockIdx.y;
+  float local = 0.f;
+  for (int n = threadIdx.x; n < n_dst; n += blockDim.x) {
+    int lo, hi;
+    float f;
+    taps(n, n_src, n_dst, lo, hi, f);
+    float a = 0.f, c = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float* r = rows + ((long)l * B + b) * n_src;
+      const float wl = weights[i * L + l];
+      a = fmaf(wl, r[lo], a);
+      c = fmaf(wl, r[hi], c);
+    }
+    const float v = a + f * (c - a);
+    w_out[((long)i * B + b) * n_dst + n] = v;
+    local += v;
+  }
+  const float tot = block_sum(local, red);
+  __syncthreads();
+  for (int n = threadIdx.x; n < n_dst; n += blockDim.x)
+    w_out[((long)i * B + b) * n_dst + n] /= tot;
+  if (threadIdx.x == 0) totals[(long)i * B + b] = tot;
+}
+
+// partial[(slice*L + l)*E + i] = sum over the slice of <Z_i, resample(T_l)>.
+// Z: (E, B, n_dst, D) fp32. Grid: (slices, L).
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+weight_grad_kernel(LayerPtrs layers, int E, const float* __restrict__ Z, int B, int n_src,
+                   int n_dst, int D, float* __restrict__ partial) {
+  __shared__ float red[32];
+  const int l = blockIdx.y;
+  const TIn* src = reinterpret_cast<const TIn*>(layers.p[l]);
+  const int groups = D >> 3;
+  const long total = (long)B * n_dst * groups;
+  const long slab = (long)B * n_dst * D;
+  float acc[MAX_E];
+#pragma unroll
+  for (int i = 0; i < MAX_E; ++i) acc[i] = 0.f;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int g = idx % groups;
+    const long tok = idx / groups;
+    const int n = tok % n_dst;
+    const int b = tok / n_dst;
+    int lo, hi;
+    float f;
+    taps(n, n_src, n_dst, lo, hi, f);
+    float v[8];
+    const long off_lo = ((long)b * n_src + lo) * D + g * 8;
+    const long off_hi = ((long)b * n_src + hi) * D + g * 8;
+    if (sizeof(TIn) == 2) {
+      load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_lo, v);
+      if (f != 0.f) {
+        float u[8];
+        load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_hi, u);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(f, u[c] - v[c], v[c]);
+      }
+    } else {
+      const float* p = reinterpret_cast<const float*>(src);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = p[off_lo + c];
+      if (f != 0.f) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(f, p[off_hi + c] - v[c], v[c]);
+      }
+    }
+    const long o = ((long)b * n_dst + n) * D + g * 8;
+#pragma unroll
+    for (int i = 0; i < MAX_E; ++i) {
+      if (i < E) {
+        const float4* z = reinterpret_cast<const float4*>(Z + (long)i * slab + o);
+        const float4 z0 = __ldg(z), z1 = __ldg(z + 1);
+        float s = acc[i];
+        s = fmaf(z0.x, v[0], s); s = fmaf(z0.y, v[1], s); s = fmaf(z0.z, v[2], s); s = fmaf(z0.w, v[3], s);
+        s = fmaf(z1.x, v[4], s); s = fmaf(z1.y, v[5], s); s = fmaf(z1.z, v[6], s); s = fmaf(z1.w, v[7], s);
+        acc[i] = s;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAX_E; ++i) {
+    if (i < E) {
+      const float s = block_sum(acc[i], red);
+      if (threadIdx.x == 0) partial[((long)blockIdx.x * gridDim.y + l) * E + i] = s;
+    }
+  }
+}
+
+// d_weights[i,l] = sum_slices partial + sum_{b,n} gw[i,b,n] * resample(rows[l,b,:])[n]
+__global__ void weight_grad_finish_kernel(const float* __restrict__ partial, int slices,
+                                          const float* __restrict__ gw,
+                                          const float* __restrict__ rows, int E, int L, int B,
+                                          int n_src, int n_dst, float gw_scale,
+                                          const float* __restrict__ gw_scale_dev,
+                                          float* __restrict__ d_weights) {
+  __shared__ float red[32];
+  const int l = blockIdx.x, i = blockIdx.y;
+  float s = 0.f, t = 0.f;
+  for (int sl = threadIdx.x; sl < slices; sl += blockDim.x) t += partial[((long)sl * L + l) * E + i];
+  for (long idx = threadIdx.x; idx < (long)B * n_dst; idx += blockDim.x) {
+    const int n = idx % n_dst;
+    const int b = idx / n_dst;
+    int lo, hi;
+    float f;
+    taps(n, n_src, n_dst, lo, hi, f);
+    const float* r = rows + ((long)l * B + b) * n_src;
+    const float v = r[lo] + f * (r[hi] - r[lo]);
+    s = fmaf(gw[((long)i * B + b) * n_dst + n], v, s);
+  }
+  if (gw_scale_dev) gw_scale *= *gw_scale_dev;
+  s = block_sum(fmaf(gw_scale, s, t), red);
+  if (threadIdx.x == 0) d_weights[i * L + l] = s;
+}
+
+}  // namespace basd
+
+using namespace basd;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int basd_attn_rows(const void* attn, int dtype, int B, int H, int side, int has_cls,
+                              float* rows, void* stream) {
+  const int n_tok = has_cls ? side - 1 : side;
+  if (dtype == BASD_DTYPE_BF16)
+    attn_rows_kernel<__nv_bfloat16><<<B, 256, 0, ST>>>((const __nv_bfloat16*)attn, H, side, has_cls,
+                                                       n_tok, rows);
+  else
+    attn_rows_kernel<float><<<B, 256, 0, ST>>>((const float*)attn, H, side, has_cls, n_tok, rows);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+static int fill_layers(LayerPtrs& lp, const void* const* ptrs, int L) {
+  if (L > MAX_L) return -6;
+  for (int l = 0; l < L; ++l) lp.p[l] = ptrs[l];
+  return 0;
+}
+
+// out: (E, B, n_dst, D) in out_dtype. teacher_layers: host array of L device pointers.
+extern "C" int basd_mix_interp(const void* const* teacher_layers, int L, int E, const float* weights,
+                               int in_dtype, int B, int n_src, int n_dst, int D, void* out,
+                               int out_dtype, void* stream) {
+  if (E > MAX_E || (D & 7)) return -7;
+  LayerPtrs lp;
+  if (int rc = fill_layers(lp, teacher_layers, L)) return rc;
+  const long total = (long)B * n_dst * (D >> 3);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (in_dtype == BASD_DTYPE_BF16 && out_dtype == BASD_DTYPE_BF16)
+    mix_interp_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, ST>>>(
+        lp, L, E, weights, B, n_src, n_dst, D, (__nv_bfloat16*)out);
+  else if (in_dtype == BASD_DTYPE_BF16)
+    mix_interp_kernel<__nv_bfloat16, float><<<grid, 256, 0, ST>>>(lp, L, E, weights, B, n_src, n_dst,
+                                                                  D, (float*)out);
+  else if (out_dtype == BASD_DTYPE_F32)
+    mix_interp_kernel<float, float><<<grid, 256, 0, ST>>>(lp, L, E, weights, B, n_src, n_dst, D,
+                                                          (float*)out);
+  else
+    return -8;
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_mix_rows(const float* rows, const float* weights, int E, int L, int B, int n_src,
+                             int n_dst, float* w_out, float* totals, void* stream) {
+  dim3 grid(B, E);
+  mix_rows_kernel<<<grid, 128, 0, ST>>>(rows, weights, L, B, n_src, n_dst, w_out, totals);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_weight_grad_slices(void) { return 148 * 2; }
+
+// partial: (slices, L, E) scratch, d_weights: (E, L).
+extern "C" int basd_weight_grad(const void* const* teacher_layers, int L, int E, const float* Z,
+                                const float* gw, const float* rows, int in_dtype, int B, int n_src,
+                                int n_dst, int D, float gw_scale, const float* gw_scale_dev,
+                                float* partial, float* d_weights, void* stream) {
+  if (E > MAX_E || (D & 7)) return -7;
+  LayerPtrs lp;
+  if (int rc = fill_layers(lp, teacher_layers, L)) return rc;
+  const int slices = basd_weight_grad_slices();
+  dim3 grid(slices, L);
+  if (in_dtype == BASD_DTYPE_BF16)
+    weight_grad_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>(lp, E, Z, B, n_src, n_dst, D, partial);
+  else
+    weight_grad_kernel<float><<<grid, 256, 0, ST>>>(lp, E, Z, B, n_src, n_dst, D, partial);
+  BASD_LAUNCH_CHECK();
+  dim3 fgrid(L, E);
+  weight_grad_finish_kernel<<<fgrid, 256, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_src, n_dst,
+                                                   gw_scale, gw_scale_dev, d_weights);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,282 @@
+// Small device-side pieces of the Grassmannian layer selector.  Everything here is O(D^2)
+// per matrix at most; the heavy lifting is in gemm_*.cu and jacobi.cu.  No host syncs: the
+// Marchenko-Pastur ranks live in device memory and downstream kernels read them there
+// (the reference syncs the host twice per teacher layer, layer_selector.py:17,19).
+#include "common.cuh"
+#include <math.h>
+
+namespace basd {
+
+// K = sym(G) - inv_rows * c c^T      (reference: layer_selector.py:35,91 centring, in Gram form)
+__global__ void center_gram_kernel(const float* __restrict__ G, const float* __restrict__ c,
+                                   int D, float inv_rows, float* __restrict__ K) {
+  const int prob = blockIdx.y;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)D * D) return;
+  const int i = idx / D, j = idx % D;
+  const float* g = G + (long)prob * D * D;
+  float v = 0.5f * (g[(long)i * D + j] + g[(long)j * D + i]);
+  if (c) v -= inv_rows * c[(long)prob * D + i] * c[(long)prob * D + j];
+  K[(long)prob * D * D + idx] = v;
+}
+
+// MP rank of each teacher layer from the spectrum of the uncentred second moment
+// (reference: layer_selector.py:8-20 and :74).  lam: (L, D) in any order.
+__global__ void mp_rank_kernel(const float* __restrict__ lam, int D, float aspect /* D/M */,
+                               int cap, int* __restrict__ ranks, float* __restrict__ edges) {
+  extern __shared__ float v[];
+  __shared__ float median;
+  __shared__ int count;
+  const int layer = blockIdx.x;
+  const float* l = lam + (long)layer * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) v[i] = l[i];
+  if (threadIdx.x == 0) count = 0;
+  __syncthreads();
+  const int want = (D - 1) / 2;   // torch.median: lower middle of the ascending order
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    int below = 0;
+    const float mine = v[i];
+    for (int j = 0; j < D; ++j) below += (v[j] < mine) || (v[j] == mine && j < i);
+    if (below == want) median = mine;
+  }
+  __syncthreads();
+  const float root = 1.f + sqrtf(aspect);
+  const float edge = median * root * root;
+  int local = 0;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) local += (v[i] > edge);
+  atomicAdd(&count, local);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ranks[layer] = min(count, cap);
+    if (edges) { edges[2 * layer] = median; edges[2 * layer + 1] = edge; }
+  }
+}
+
+// dims[i*L + l] = ranks[l]
+__global__ void expand_ranks_kernel(const int* __restrict__ ranks, int E, int L,
+                                    int* __restrict__ dims) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < E * L) dims[idx] = ranks[idx % L];
+}
+
+// Zero everything outside the leading dims[prob] x dims[prob] block; src may equal dst.
+__global__ void mask_block_kernel(const float* __restrict__ src, float* __restrict__ dst, int D,
+                                  const int* __restrict__ dims) {
+  const int prob = blockIdx.y;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)D * D) return;
+  const int k = dims[prob];
+  const int i = idx / D, j = idx % D;
+  const long off = (long)prob * D * D + idx;
+  dst[off] = (i < k && j < k) ? src[off] : 0.f;
+}
+
+// Spectrally weighted squared Grassmann distance (reference: layer_selector.py:100-105).
+// sig: (E*L, D) principal-angle cosines (descending), lam_c: (L, D) centred teacher
+// eigenvalues (descending) -> sw = sqrt(lam).
+__global__ void angle_distance_kernel(const float* __restrict__ sig, const float* __restrict__ lam_c,
+                                      const int* __restrict__ ranks, int D, int L,
+                                      float* __restrict__ dist) {
+  __shared__ float red[32];
+  const int prob = blockIdx.x, layer = prob % L;
+  const int k = ranks[layer];
+  const float lim = 1.f - 1.1920929e-07f;
+  float num = 0.f, den = 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const float sw = sqrtf(fmaxf(lam_c[(long)layer * D + j], 0.f));
+    const float th = acosf(fminf(sig[(long)prob * D + j], lim));
+    num = fmaf(sw, th * th, num);
+    den += sw;
+  }
+  num = block_sum(num, red);
+  den = block_sum(den, red);
+  if (threadIdx.x == 0) dist[prob] = num / den;   // k == 0 -> 0/0 = NaN like the reference
+}
+
+// weights[i,:] = softmax(-dist[i,:] / softplus(log_temp[i]))   (reference: :67,:107-108)
+__global__ void mix_weights_kernel(const float* __restrict__ dist, const float* __restrict__ log_temp,
+                                   int L, float* __restrict__ weights, float* __restrict__ temps) {
+  const int i = blockIdx.x;
+  const float x = log_temp[i];
+  const float tau = (x > 20.f) ? x : log1pf(expf(x));
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int l = 0; l < L; ++l) mx = fmaxf(mx, -dist[i * L + l] / tau);
+    float z = 0.f;
+    for (int l = 0; l < L; ++l) z += expf(-dist[i * L + l] / tau - mx);
+    for (int l = 0; l < L; ++l) weights[i * L + l] = expf(-dist[i * L + l] / tau - mx) / z;
+    temps[i] = tau;
+  }
+}
+
+// Backward of softmax(-d/tau), tau = softplus(log_temp):
+//   d_dist (E,L), d_log_temp (E)      (autograd of layer_selector.py:107-108)
+__global__ void mix_weights_bwd_kernel(const float* __restrict__ d_weights,
+                                       const float* __restrict__ weights,
+                                       const float* __restrict__ dist,
+                                       const float* __restrict__ log_temp, int L, float scale,
+                                       float* __restrict__ d_dist, float* __restrict__ d_log_temp) {
+  const int i = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const float x = log_temp[i];
+  const float tau = (x > 20.f) ? x : log1pf(expf(x));
+  float dot = 0.f;
+  for (int l = 0; l < L; ++l) dot += weights[i * L + l] * d_weights[i * L + l];
+  float d_tau = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float dy = weights[i * L + l] * (d_weights[i * L + l] - dot);
+    d_dist[i * L + l] = -dy / tau;
+    d_tau += dy * dist[i * L + l];
+  }
+  d_tau /= tau * tau;
+  d_log_temp[i] = scale * d_tau / (1.f + expf(-x));
+}
+
+// Scales the rows of Uxt (E*L, D, D) by d sigma_m (autograd of acos/clamp/pow/weighted mean,
+// layer_selector.py:100-105): row m *= d_dist * sw_m/sum(sw) * 2 theta_m * (-1/sqrt(1-s^2)).
+__global__ void scale_rows_dsigma_kernel(float* __restrict__ Uxt, const float* __restrict__ sig,
+                                         const float* __restrict__ lam_c,
+                                         const int* __restrict__ ranks,
+                                         const float* __restrict__ d_dist, int D, int L) {
+  __shared__ float red[32];
+  const int prob = blockIdx.x, layer = prob % L;
+  const int k = ranks[layer];
+  float den = 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x)
+    den += sqrtf(fmaxf(lam_c[(long)layer * D + j], 0.f));
+  den = block_sum(den, red);
+  const float lim = 1.f - 1.1920929e-07f;
+  const float dd = d_dist[prob];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int m = warp; m < D; m += nw) {
+    float f = 0.f;
+    if (m < k) {
+      const float s = sig[(long)prob * D + m];
+      if (s < lim) {
+        const float sw = sqrtf(fmaxf(lam_c[(long)layer * D + m], 0.f));
+        const float th = acosf(s);
+        f = dd * (sw / den) * 2.f * th * (-rsqrtf(fmaxf(1.f - s * s, 1e-30f)));
+      }
+    }
+    float* row = Uxt + ((long)prob * D + m) * D;
+    for (int a = lane; a < D; a += 32) row[a] *= f;
+  }
+}
+
+// Omega_i[j,a] = sum_l [a < k_l <= j] block_l[j,a] / (lam_a - lam_j)   
+// block: (E*L, D, D); lam_s: (E, D) descending student eigenvalues; out: (E, D, D).
+__global__ void omega_accumulate_kernel(const float* __restrict__ block,
+                                        const float* __restrict__ lam_s,
+                                        const int* __restrict__ ranks, int D, int L,
+                                        float* __restrict__ omega) {
+  const int i = blockIdx.y;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)D * D) return;
+  const int j = idx / D, a = idx % D;
+  float acc = 0.f;
+  if (j > a) {
+    const float gap = lam_s[(long)i * D + a] - lam_s[(long)i * D + j];
+    const float inv = (gap > 0.f) ? 1.f / gap : 0.f;
+    for (int l = 0; l < L; ++l) {
+      const int k = ranks[l];
+      if (a < k && k <= j) acc += block[((long)(i * L + l) * D + j) * D + a];
+    }
+    acc *= inv;
+  }
+  omega[(long)i * D * D + idx] = acc;
+}
+
+// out = in + in^T (per matrix)
+__global__ void symmetrize_add_kernel(const float* __restrict__ in, int D, float* __restrict__ out) {
+  const int prob = blockIdx.y;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)D * D) return;
+  const int i = idx / D, j = idx % D;
+  const float* m = in + (long)prob * D * D;
+  out[(long)prob * D * D + idx] = m[(long)i * D + j] + m[(long)j * D + i];
+}
+
+}  // namespace basd
+
+using namespace basd;
+#define ST ((cudaStream_t)stream)
+static inline unsigned blocks_for(long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+extern "C" int basd_center_gram(const float* G, const float* colsum, int D, float inv_rows,
+                                float* K, int batch, void* stream) {
+  if (batch <= 0) return 0;
+  dim3 grid(blocks_for((long)D * D, 256), batch);
+  center_gram_kernel<<<grid, 256, 0, ST>>>(G, colsum, D, inv_rows, K);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_mp_rank(const float* lam, int D, long rows, int cap, int* ranks, float* edges,
+                            int layers, void* stream) {
+  if (layers <= 0) return 0;
+  mp_rank_kernel<<<layers, 256, D * sizeof(float), ST>>>(lam, D, (float)((double)D / (double)rows),
+                                                         cap, ranks, edges);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_expand_ranks(const int* ranks, int E, int L, int* dims, void* stream) {
+  expand_ranks_kernel<<<blocks_for(E * L, 128), 128, 0, ST>>>(ranks, E, L, dims);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_mask_block(const float* src, float* dst, int D, const int* dims, int batch,
+                               void* stream) {
+  if (batch <= 0) return 0;
+  dim3 grid(blocks_for((long)D * D, 256), batch);
+  mask_block_kernel<<<grid, 256, 0, ST>>>(src, dst, D, dims);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_angle_distance(const float* sig, const float* lam_c, const int* ranks, int D,
+                                   int E, int L, float* dist, void* stream) {
+  angle_distance_kernel<<<E * L, 128, 0, ST>>>(sig, lam_c, ranks, D, L, dist);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_mix_weights(const float* dist, const float* log_temp, int E, int L,
+                                float* weights, float* temps, void* stream) {
+  mix_weights_kernel<<<E, 32, 0, ST>>>(dist, log_temp, L, weights, temps);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_mix_weights_bwd(const float* d_weights, const float* weights, const float* dist,
+                                    const float* log_temp, int E, int L, float scale, float* d_dist,
+                                    float* d_log_temp, void* stream) {
+  mix_weights_bwd_kernel<<<E, 32, 0, ST>>>(d_weights, weights, dist, log_temp, L, scale, d_dist,
+                                          d_log_temp);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_scale_rows_dsigma(float* Uxt, const float* sig, const float* lam_c,
+                                      const int* ranks, const float* d_dist, int D, int E, int L,
+                                      void* stream) {
+  scale_rows_dsigma_kernel<<<E * L, 256, 0, ST>>>(Uxt, sig, lam_c, ranks, d_dist, D, L);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_omega_accumulate(const float* block, const float* lam_s, const int* ranks, int D,
+                                     int E, int L, float* omega, void* stream) {
+  dim3 grid(blocks_for((long)D * D, 256), E);
+  omega_accumulate_kernel<<<grid, 256, 0, ST>>>(block, lam_s, ranks, D, L, omega);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_symmetrize_add(const float* in, int D, float* out, int batch, void* stream) {
+  dim3 grid(blocks_for((long)D * D, 256), batch);
+  symmetrize_add_kernel<<<grid, 256, 0, ST>>>(in, D, out);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}

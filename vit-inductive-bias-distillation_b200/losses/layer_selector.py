@@ -1,0 +1,162 @@
+"""Grassmannian layer selector on the B200 kernels.
+
+Interface mirror of the reference's ``src/losses/layer_selector.py`` (class at :40-152,
+``marchenko_pastur_rank`` at :8-20): same constructor, buffers (``proj_s``, ``proj_t``),
+parameter (``log_temperatures``), ``temperatures`` property, ``subspace_ranks`` side effect
+and ``forward`` signature.  The arithmetic runs in libbasd_b200.so.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _engine as eng
+from .._autograd import MixingWeights, StepContext, world_size
+from .._native import call, ptr, stream
+
+
+@torch.no_grad()
+def marchenko_pastur_rank(features: torch.Tensor) -> int:
+    """MP rank of an (M, D) feature matrix on the device kernels (reference :8-20).
+
+    Returns a python int like the reference, which costs one host sync here (the loss's
+    own forward keeps the ranks on the device and never syncs)."""
+    if features.dim() != 2:
+        raise ValueError("features must be (M, D)")
+    rows, dim = features.shape
+    if rows < dim:
+        raise ValueError("marchenko_pastur_rank: the M < D branch (reference :14-15) is not built")
+    x = features.contiguous()
+    gram = torch.empty(1, dim, dim, dtype=torch.float32, device=x.device)
+    col = torch.empty(dim, dtype=torch.float32, device=x.device)
+    eng.token_gram(x, gram[0], col)
+    k = torch.empty_like(gram)
+    call("basd_center_gram", ptr(gram), None, dim, 0.0, ptr(k), 1, stream())
+    lam, _ = eng.sym_eig(k)
+    rank = torch.empty(1, dtype=torch.int32, device=x.device)
+    call("basd_mp_rank", ptr(lam), dim, rows, dim, ptr(rank), None, 1, stream())
+    return int(rank.item())
+
+
+class _LazyRanks(dict):
+    """``subspace_ranks`` with the reference's dict interface; the values stay on the GPU
+    until somebody reads them (the reference syncs 2 x L_t times per step to fill it)."""
+
+    def __init__(self):
+        super().__init__()
+        self._pending = None
+
+    def _stage(self, keys, ranks):
+        self._pending = (list(keys), ranks)
+
+    def _sync(self):
+        if self._pending is not None:
+            keys, ranks = self._pending
+            self._pending = None
+            for k, v in zip(keys, ranks.tolist()):
+                super().__setitem__(k, int(v))
+
+    def __getitem__(self, k):
+        self._sync()
+        return super().__getitem__(k)
+
+    def __iter__(self):
+        self._sync()
+        return super().__iter__()
+
+    def __len__(self):
+        self._sync()
+        return super().__len__()
+
+    def __contains__(self, k):
+        self._sync()
+        return super().__contains__(k)
+
+    def __eq__(self, other):
+        self._sync()
+        return dict(self.items()) == other
+
+    def __repr__(self):
+        self._sync()
+        return super().__repr__()
+
+    def keys(self):
+        self._sync()
+        return super().keys()
+
+    def values(self):
+        self._sync()
+        return super().values()
+
+    def items(self):
+        self._sync()
+        return super().items()
+
+    def get(self, k, default=None):
+        self._sync()
+        return super().get(k, default)
+
+
+class GrassmannianLayerSelector(nn.Module):
+    def __init__(self, num_extraction_points: int, student_dim: int, teacher_dim: int):
+        super().__init__()
+        self.student_dim = student_dim
+        self.subspace_ranks = _LazyRanks()
+        # same RNG consumption order as the reference (:51-56)
+        proj_s = torch.empty(student_dim, student_dim)
+        proj_t = torch.empty(student_dim, teacher_dim)
+        nn.init.orthogonal_(proj_s)
+        nn.init.orthogonal_(proj_t)
+        self.register_buffer("proj_s", proj_s)
+        self.register_buffer("proj_t", proj_t)
+        self.log_temperatures = nn.Parameter(
+            torch.full((num_extraction_points,), math.log(math.exp(1.0) - 1)))
+        self.process_group = None
+        self.sync_stats = True
+        self.last_state = None
+
+    @property
+    def temperatures(self) -> torch.Tensor:
+        return torch.nn.functional.softplus(self.log_temperatures)
+
+    def _step(self, teacher_tokens, teacher_attns, has_cls, n_student) -> StepContext:
+        keys = sorted(teacher_tokens.keys())
+        world = world_size(self.process_group) if self.sync_stats else 1
+        return StepContext(
+            teachers=[teacher_tokens[k] for k in keys], attns=[teacher_attns[k] for k in keys],
+            has_cls=has_cls, n_student=n_student, proj_s=self.proj_s.float().contiguous(),
+            proj_t=self.proj_t.float().contiguous(), group=self.process_group, world=world)
+
+    def mixing_weights(self, student_tokens_per_layer, all_teacher_tokens, all_teacher_attns,
+                       extraction_indices, *, has_cls=True, n_student=None):
+        """(E, L_t) softmax mixing weights, differentiable w.r.t. the student tokens and
+        ``log_temperatures``; also returns the StepContext the Procrustes stage reuses."""
+        students = [student_tokens_per_layer[l] for l in extraction_indices]
+        if n_student is None:
+            n_student = students[0].shape[1]
+        step = self._step(all_teacher_tokens, all_teacher_attns, has_cls, n_student)
+        weights = MixingWeights.apply(self.log_temperatures, step, *students)
+        self.subspace_ranks._stage(sorted(all_teacher_tokens.keys()), step.selector.ranks)
+        self.last_state = step.selector
+        return weights, step
+
+    def forward(self, student_tokens_per_layer, all_teacher_tokens, all_teacher_attns,
+                extraction_indices):
+        """Reference-shaped entry (:116-152): dicts of mixed teacher tokens (B,N_t,D_t) and
+        mixed attention maps keyed by student layer.  The weights come from the kernels;
+        materialising the full mixed maps is only done here, for API compatibility --
+        BASDLoss never does it."""
+        has_cls = True
+        weights, _ = self.mixing_weights(student_tokens_per_layer, all_teacher_tokens,
+                                         all_teacher_attns, extraction_indices, has_cls=has_cls)
+        keys = sorted(all_teacher_tokens.keys())
+        tok = torch.stack([all_teacher_tokens[k] for k in keys])
+        att = torch.stack([all_teacher_attns[k] for k in keys])
+        mixed_tok, mixed_att = {}, {}
+        for i, layer in enumerate(extraction_indices):
+            w = weights[i].to(tok.dtype)
+            mixed_tok[layer] = (w.view(-1, 1, 1, 1) * tok).sum(dim=0)
+            mixed_att[layer] = (w.to(att.dtype).view(-1, 1, 1, 1, 1) * att).sum(dim=0)
+        return mixed_tok, mixed_att
