@@ -118,6 +118,8 @@ def selector_backward_model(sel, d_weights, rows_s, proj_s, log_temps):
         d_gram = vec @ omega @ vec.T
         w_sym = d_gram + d_gram.T
         w_primes.append(proj_s.T @ w_sym @ proj_s)
+        saved["omega"] = omega
+        saved["d_dist"] = d_dist
     return d_logt, w_primes
 
 
@@ -288,6 +290,7 @@ def full_step_model(logits, targets, students, teachers, attns, *, layers, proj_
                                        + (g_wt[layer] * up_row(rows[j])).sum())
         grad_students[layer] = scale * g_s[layer]
     d_logt, w_primes = selector_backward_model(sel, d_weights, rows_s, proj_s, log_temps.detach())
+    grad_direct = {l: g.clone() for l, g in grad_students.items()}
     for i, layer in enumerate(layers):
         x = students[layer].float().reshape(rows_s, -1)
         centred = x - x.mean(dim=0, keepdim=True)
@@ -295,4 +298,4 @@ def full_step_model(logits, targets, students, teachers, attns, *, layers, proj_
     return dict(loss=loss.detach(), ce=ce.detach(), geo=geo.detach(), ranks=sel["ranks"],
                 weights=torch.stack(sel["weights"]), dist=torch.stack(sel["dist"]),
                 grad_students=grad_students, grad_log_temps=d_logt, grad_logits=logits.grad,
-                d_weights=d_weights)
+                d_weights=d_weights, grad_direct=grad_direct, w_primes=w_primes, sel=sel)

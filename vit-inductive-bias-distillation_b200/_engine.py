@@ -20,9 +20,11 @@ from ._native import call, ptr, stream
 
 JACOBI_TOL = 1e-6
 JACOBI_SWEEPS = 18
-CHOL_TOL = 1e-6          # pivoted-Cholesky rank cut, relative to the largest diagonal
-GRAM_CHOL_TOL = 1e-7
-SV_FLOOR = 1e-6          # singular directions below this (relative) leave the polar factor
+CHOL_TOL = 1e-5          # pivoted-Cholesky rank cut (per-sample N x N Grams), relative to the
+                         # largest diagonal: just above the fp32 accumulation noise of K
+GRAM_CHOL_TOL = 1e-7     # same for the D x D selector Grams
+SV_FLOOR = 1e-6          # k x k principal-angle SVD: directions below this are dropped
+PROC_SV_FLOOR = 2.5e-4   # Procrustes: below sqrt(eps) * sigma_max the recovered v_j is noise
 
 
 def _f32(*shape, device):
@@ -301,7 +303,7 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
     sgemm(0, 0, n, n, n, ut, n, nn, x0, n, nn, rows2, n, nn, p)        # U^T X = S V^T
     sig = _f32(p, n, device=dev)
     nuc = _f32(p, device=dev)
-    call("basd_procrustes_rows_finish", ptr(rows2), ptr(ut), n, n, nn, p, SV_FLOOR, ptr(sig),
+    call("basd_procrustes_rows_finish", ptr(rows2), ptr(ut), n, n, nn, p, PROC_SV_FLOOR, ptr(sig),
          ptr(nuc), stream())
     f = _f32(p, device=dev)
     m_a = m_b = gw = None
