@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""BASD loss fwd+bwd benchmark (BASELINE.json metric) -- see DESIGN.md §6.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--batch 256]
+  python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
+
+One "step" = one forward + backward of the loss module over one batch of synthetic,
+ImageNet-shaped DeiT-S<-DeiT-B features (C2: B=256/GPU, N=196, D 384<-768, 12 teacher
+layers, bf16 tokens, fp32 attention maps).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import basd_b200.synthetic as syn  # noqa: E402
+
+METRIC = "basd_loss_fwd_bwd_samples_per_sec"
+UNIT = "samples/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    sm_max_mhz=p["sm_max_mhz"], source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def build_module(work, device, impl="b200"):
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=1.0 / work.num_classes)
+    cfg = types.SimpleNamespace(num_extraction_points=work.num_points)
+    torch.manual_seed(0)
+    if impl == "b200":
+        from basd_b200.losses import BASDLoss
+        mod = BASDLoss(crit, work.d_student, work.d_teacher, work.student_depth, work.n_student,
+                       config=cfg, teacher_has_cls_token=work.has_cls)
+    else:
+        from oracle.ref_port import OracleBASD
+        mod = OracleBASD(crit, work.d_student, work.d_teacher, work.student_depth, work.n_student,
+                         config=cfg, teacher_has_cls_token=work.has_cls)
+    return mod.to(device)
+
+
+def one_step(mod, logits, targets, st, te, at):
+    for v in st.values():
+        v.grad = None
+    logits.grad = None
+    mod.layer_selector.log_temperatures.grad = None
+    loss = mod(logits, targets, st, te, at)
+    loss.backward()
+    return loss
+
+
+# ------------------------------------------------------------------ roofline leg
+def flop_model(work, ranks_mean):
+    """Algorithmic work of the formulation the kernels actually use."""
+    b, n, ds, dt, l, e = work.batch, work.n_student, work.d_student, work.d_teacher, work.teacher_layers, work.num_points
+    m_s, m_t = b * work.n_student, b * work.n_teacher
+    gram = 2.0 * m_t * dt * dt * l / 2 + 2.0 * m_s * ds * ds * e / 2     # symmetric token-space Grams
+    mix_bytes = (l * b * work.n_teacher * dt + e * b * n * dt) * 2.0
+    return dict(gram_flops=gram, mix_bytes=mix_bytes)
+
+
+def roofline(work, mod, args5, pk, clocks):
+    """Per-entry-point CUDA-event timing of one extra (untimed) step; returns the roofline
+    record of the dominant kernel plus a per-kernel table."""
+    from basd_b200 import _native as nat
+    one_step(mod, *args5)
+    torch.cuda.synchronize()
+    nat.start_timeline()
+    one_step(mod, *args5)
+    tl = nat.stop_timeline()
+    if os.environ.get("BASD_TIMELINE"):
+        with open(os.environ["BASD_TIMELINE"], "w") as fh:
+            for name, ms in tl:
+                fh.write(f"{name},{ms:.4f}\n")
+    agg = {}
+    for name, ms in tl:
+        agg.setdefault(name, [0.0, 0])
+        agg[name][0] += ms
+        agg[name][1] += 1
+    total = sum(v[0] for v in agg.values())
+    table = sorted(((k, v[0], v[1]) for k, v in agg.items()), key=lambda x: -x[1])
+    fm = flop_model(work, None)
+    sm_mhz = clocks.get("sm_mhz") or pk["sm_max_mhz"]
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    records = []
+    for name, ms, cnt in table:
+        rec = {"kernel": name, "ms": round(ms, 4), "launches": cnt, "share": round(ms / total, 4)}
+        if name in ("basd_token_gram_simt", "basd_token_gram_tc"):
+            rec.update(bound="tensor" if name.endswith("tc") else "fp32", achieved=fm["gram_flops"] / (ms * 1e-3) / 1e12,
+                       peak=pk["bf16_sustained"] if name.endswith("tc") else fp32_peak, unit="TFLOP/s")
+        elif name == "basd_mix_interp":
+            rec.update(bound="hbm", achieved=fm["mix_bytes"] / (ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s")
+        if "achieved" in rec:
+            rec["frac"] = rec["achieved"] / rec["peak"]
+        records.append(rec)
+    return records, total, fp32_peak
+
+
+def run_b200(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    work = syn.scaled(syn.WORKLOADS[args.workload], args.batch)
+    mod = build_module(work, device)
+    logits, targets, st, te, at = syn.make_inputs_fast(work, seed=rank, device=device)
+    st = {k: v.requires_grad_(True) for k, v in st.items()}
+    logits.requires_grad_(True)
+    args5 = (logits, targets, st, te, at)
+    from basd_b200 import _native as nat
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step(mod, *args5)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = nat.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = one_step(mod, *args5)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = nat.launch_count - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    clocks = sampler.summary()
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = work.batch * world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end leg: host (pinned) inputs -> device copy -> fwd+bwd -> loss back on host
+    host = {
+        "st": {k: v.detach().cpu().pin_memory() for k, v in st.items()},
+        "te": {k: v.cpu().pin_memory() for k, v in te.items()},
+        # the loss reads only the CLS row (mean over heads is done on device): copy just that
+        "at": {k: (v[:, :, 0, :].contiguous() if work.has_cls else v).cpu().pin_memory() for k, v in at.items()},
+        "logits": logits.detach().cpu().pin_memory(), "targets": targets.cpu().pin_memory(),
+    }
+    h2d = sum(v.numel() * v.element_size() for d in (host["st"], host["te"], host["at"]) for v in d.values())
+    h2d += host["logits"].numel() * 4 + host["targets"].numel() * 8
+
+    def e2e_step():
+        st_d = {k: v.to(device, non_blocking=True).requires_grad_(True) for k, v in host["st"].items()}
+        te_d = {k: v.to(device, non_blocking=True) for k, v in host["te"].items()}
+        if work.has_cls:   # (B,H,side) CLS rows -> importance rows (B,Nt): tiny device-side mean
+            at_d = {k: v.to(device, non_blocking=True)[:, :, 1:].mean(dim=1) for k, v in host["at"].items()}
+        else:
+            at_d = {k: v.to(device, non_blocking=True) for k, v in host["at"].items()}
+        lg = host["logits"].to(device, non_blocking=True).requires_grad_(True)
+        tg = host["targets"].to(device, non_blocking=True)
+        loss = mod(lg, tg, st_d, te_d, at_d)
+        loss.backward()
+        return float(loss.detach().cpu())
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = work.batch * world / (float(t.item()) * 1e-3)
+
+    pk = peaks()
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": work.name, "batch_per_gpu": work.batch, "student_tokens": work.n_student,
+                   "teacher_tokens": work.n_teacher, "student_dim": work.d_student,
+                   "teacher_dim": work.d_teacher, "teacher_layers": work.teacher_layers,
+                   "token_dtype": str(work.token_dtype).replace("torch.", ""),
+                   "cache": "inputs (>=1 GB tokens + attention maps per step) exceed the 126 MB L2",
+                   "parallelism": f"dp{world}"},
+        "clocks": clocks, "gpu_launches": launches // max(1, args.steps),
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 4, "ms_per_step": round(float(t.item()), 3)},
+    }
+    if rank == 0:
+        records, total, fp32_peak = roofline(work, mod, args5, pk, clocks)
+        line["kernels"] = records[:12]
+        line["kernel_ms_total"] = round(total, 3)
+        top = next((r for r in records if "achieved" in r), None)
+        if top:
+            line["roofline"] = {"kernel": top["kernel"], "bound": top["bound"], "achieved": round(top["achieved"], 2),
+                                "peak": round(top["peak"], 2), "unit": top["unit"], "frac": round(top["frac"], 4),
+                                "traffic": None, "peak_source": pk["source"]}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, sample_batch=args.cpu_batch, steps=1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ CPU arms
+def cpu_baseline(args, sample_batch, steps):
+    """The reference algorithm (oracle port: same torch.linalg calls as the reference) on the
+    host cores, on a bounded sample of the workload."""
+    torch.set_num_threads(os.cpu_count())
+    work = syn.scaled(syn.WORKLOADS[args.workload], sample_batch)
+    mod = build_module(work, "cpu", impl="reference")
+    logits, targets, st, te, at = syn.make_inputs_fast(work, seed=0, device="cpu")
+    st = {k: v.float().requires_grad_(True) for k, v in st.items()}
+    te = {k: v.float() for k, v in te.items()}
+    logits.requires_grad_(True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for v in st.values():
+            v.grad = None
+        loss = mod(logits, targets, st, te, at)
+        loss.backward()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(sample_batch / dt, 3), "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{steps} step(s) of {work.name} (batch {sample_batch} of the "
+            f"workload's {args.batch}; the reference scales ~linearly in batch), fp32, autocast off",
+            "seconds_per_step": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    work = syn.scaled(syn.WORKLOADS[args.workload], args.cpu_batch)
+    mod = build_module(work, "cpu", impl="reference")
+    logits, targets, st, te, at = syn.make_inputs_fast(work, seed=0, device="cpu")
+    st = {k: v.float().requires_grad_(True) for k, v in st.items()}
+    te = {k: v.float() for k, v in te.items()}
+    logits.requires_grad_(True)
+
+    def step():
+        for v in st.values():
+            v.grad = None
+        loss = mod(logits, targets, st, te, at)
+        loss.backward()
+
+    steps, warm = min(args.steps, 3), min(args.warmup, 1)
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = args.cpu_batch / dt
+    full = syn.scaled(syn.WORKLOADS[args.workload], args.batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
+        "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": full.name, "batch_per_gpu": full.batch, "student_tokens": full.n_student,
+                   "teacher_tokens": full.n_teacher, "student_dim": full.d_student,
+                   "teacher_dim": full.d_teacher, "teacher_layers": full.teacher_layers,
+                   "token_dtype": "float32 (bf16 tokens upcast: the reference cannot take bf16)",
+                   "parallelism": "cpu"},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} step(s) at batch {args.cpu_batch} of the workload's {args.batch} "
+                                   "(bounded sample; samples/s is ~flat in batch)"},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(syn.WORKLOADS))
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@ CHOL_TOL = 1e-5          # pivoted-Cholesky rank cut (per-sample N x N Grams), r
                          # largest diagonal: just above the fp32 accumulation noise of K
 GRAM_CHOL_TOL = 1e-7     # same for the D x D selector Grams
 SV_FLOOR = 1e-6          # k x k principal-angle SVD: directions below this are dropped
+ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerically zero in fp32
 PROC_SV_FLOOR = 2.5e-4   # Procrustes: below sqrt(eps) * sigma_max the recovered v_j is noise
 
 
@@ -85,7 +86,7 @@ def sym_eig(kmats: torch.Tensor):
     jacobi_rows(lt)
     vt = work                         # reuse: the Schur complement is dead
     coarse = _f32(batch, d, device=dev)
-    rows_normalize(lt, vt, coarse, sort=True, square=True, rel_floor=0.0)
+    rows_normalize(lt, vt, coarse, sort=True, square=True, rel_floor=ROW_FLOOR)
     kv = lt                           # reuse
     sgemm(0, 0, d, d, d, vt, d, d * d, kmats, d, d * d, kv, d, d * d, batch)
     lam = _f32(batch, d, device=dev)
@@ -297,7 +298,7 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
     sgemm(0, 1, n, n, n, lt_t, n, nn, ls_t, n, nn, g, n, nn, p)       # X^T
     sweeps = torch.zeros(p, dtype=torch.int32, device=dev)
     jacobi_rows(g, sweeps_out=sweeps)                    # rows -> sigma_j u_j^T
-    rows_normalize(g, g, None, sort=False, square=False, rel_floor=0.0)
+    rows_normalize(g, g, None, sort=False, square=False, rel_floor=ROW_FLOOR)
     ut = g
     rows2 = _f32(p, n, n, device=dev)
     sgemm(0, 0, n, n, n, ut, n, nn, x0, n, nn, rows2, n, nn, p)        # U^T X = S V^T

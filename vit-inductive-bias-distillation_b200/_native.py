@@ -115,8 +115,37 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-call CUDA-event timing (bench.py's roofline leg): when `_timeline` is a list,
+# every C-ABI call is bracketed by events recorded on the launching stream.
+_timeline = None
+launch_count = 0
+
+
+def start_timeline():
+    global _timeline
+    _timeline = []
+
+
+def stop_timeline():
+    """Returns [(entry point, milliseconds)] for the calls since start_timeline()."""
+    global _timeline
+    tl, _timeline = _timeline, None
+    torch.cuda.synchronize()
+    return [(n, a.elapsed_time(b)) for n, a, b in tl]
+
+
 def call(name: str, *args):
-    rc = getattr(load(), name)(*args)
+    global launch_count
+    launch_count += 1
+    if _timeline is not None:
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(load(), name)(*args)
+        b.record()
+        _timeline.append((name, a, b))
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != 0:
         msg = f"{name} failed with code {rc}"
         if rc > 0:

@@ -13,6 +13,7 @@
 // row-Jacobi = Veselic-Hari), the k x k principal-angle SVDs (layer_selector.py:99) and the
 // per-sample Procrustes SVD (relational.py:48, reduced to N x N).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace basd {
 
@@ -29,15 +30,20 @@ __global__ void pivoted_cholesky_kernel(float* __restrict__ Kbase, int n, int ld
   float* Kg = Kbase + (long)prob * strideK;
   float* LT = LTbase + (long)prob * strideL;
   const int nn = dims ? min(dims[prob], n) : n;
-  float* colv = smem;                // n
-  float* diag = colv + n;            // n
-  float* red = diag + n;             // 64
+  const int npad = (n + 3) & ~3;
+  float* colv = smem;                // npad (zero beyond nn)
+  float* diag = colv + npad;         // npad
+  float* red = diag + npad;          // 64
   int* redi = reinterpret_cast<int*>(red + 64);  // 64
-  float* As = red + 128;             // n*n when staged
+  float* As = red + 128;             // npad*npad when staged
   float* A = use_smem ? As : Kg;
-  const int lda = use_smem ? nn : ld;
-  if (use_smem)
-    for (int e = tid; e < nn * nn; e += T) As[e] = Kg[(long)(e / nn) * ld + (e % nn)];
+  const int lda = use_smem ? ((nn + 3) & ~3) : ld;
+  if (use_smem) {
+    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    for (int r = warp; r < nn; r += nwarp)
+      for (int c = lane; c < lda; c += 32) As[r * lda + c] = (c < nn) ? Kg[(long)r * ld + c] : 0.f;
+  }
+  for (int i = tid; i < npad; i += T) colv[i] = 0.f;
   __syncthreads();
   float dmax = 0.f;
   for (int i = tid; i < nn; i += T) {
@@ -80,10 +86,21 @@ __global__ void pivoted_cholesky_kernel(float* __restrict__ Kbase, int n, int ld
       LT[(long)j * ldl + i] = c;
     }
     __syncthreads();
-    for (int e = tid; e < nn * nn; e += T) {
-      const int i = e / nn, k = e - i * nn;
-      const float ci = colv[i], ck = colv[k];
-      if (ci != 0.f && ck != 0.f) A[(long)i * lda + k] -= ci * ck;
+    {   // rank-1 update A -= col col^T, one warp per row, 128-bit column chunks
+      const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+      const int quads = lda >> 2;                 // lda % 4 == 0 on both paths
+      for (int i = warp; i < nn; i += nwarp) {
+        const float ci = colv[i];
+        if (ci == 0.f) continue;                  // eliminated row: nothing to do
+        float4* row = reinterpret_cast<float4*>(A + (long)i * lda);
+        for (int k4 = lane; k4 < quads; k4 += 32) {
+          const float4 ck = *reinterpret_cast<const float4*>(colv + 4 * k4);
+          float4 a = row[k4];
+          a.x = fmaf(-ci, ck.x, a.x); a.y = fmaf(-ci, ck.y, a.y);
+          a.z = fmaf(-ci, ck.z, a.z); a.w = fmaf(-ci, ck.w, a.w);
+          row[k4] = a;
+        }
+      }
     }
     for (int i = tid; i < nn; i += T) {
       if (i == p) diag[i] = -1.f;
@@ -210,6 +227,141 @@ jacobi_rows_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
   if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
 }
 
+// Shared-memory variant with LP lanes per row pair (LP = 8 or 16): 32/LP pairs per warp, so a
+// whole round-robin step of an N<=224 problem runs in ONE round of the CTA instead of four.
+// Squared row norms are cached in shared memory and updated analytically after each rotation
+// (a_pp' = a_pp - t*g, a_qq' = a_qq + t*g), refreshed at the start of every sweep, so a pair
+// costs one dot product instead of three; the rotation parameters use one fast divide and
+// one rsqrt (+ a Newton step on c so that c^2 + s^2 = 1 to an ulp).
+template <int LP, int NV, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+jacobi_rows_grouped_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                           const int* __restrict__ dims, float tol, int max_sweeps,
+                           int* __restrict__ sweeps_out) {
+  extern __shared__ __align__(16) float smem[];
+  const int prob = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int gid = tid / LP, gl = tid % LP, groups = T / LP;
+  float* Gg = Gbase + (long)prob * stride;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
+  const int mv = (mm + 3) >> 2;
+  const int ldw = mv * 4;
+  __shared__ float red_scratch[32];
+  float* G = smem;
+  float* nrm2 = smem + (size_t)n * (((size_t)m + 3) & ~(size_t)3);
+  for (int e = tid; e < nn * mv; e += T) {
+    const int r = e / mv, c4 = (e - r * mv) * 4;
+    float4 v = *reinterpret_cast<const float4*>(Gg + (long)r * ld + c4);
+    if (c4 + 1 >= mm) v.y = 0.f;
+    if (c4 + 2 >= mm) v.z = 0.f;
+    if (c4 + 3 >= mm) v.w = 0.f;
+    *reinterpret_cast<float4*>(G + (long)r * ldw + c4) = v;
+  }
+  __syncthreads();
+  const int ne = nn + (nn & 1), ring = ne - 1, half = ne >> 1;
+  const float tol2 = tol * tol;
+  int sweep = 0;
+  for (; sweep < max_sweeps && nn >= 2; ++sweep) {
+    for (int base = 0; base < nn; base += groups) {        // refresh the cached norms
+      const int r = base + gid;
+      float a = 0.f;
+      if (r < nn) {
+        const float4* row = reinterpret_cast<const float4*>(G + (long)r * ldw);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int idx = gl + LP * v;
+          if (idx < mv) {
+            const float4 x = row[idx];
+            a = fmaf(x.x, x.x, a); a = fmaf(x.y, x.y, a); a = fmaf(x.z, x.z, a); a = fmaf(x.w, x.w, a);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = LP >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (r < nn && gl == 0) nrm2[r] = a;
+    }
+    __syncthreads();
+    // rows more than 1e-7 below the largest row are numerically zero: never rotate them
+    float mx = 0.f;
+    for (int r = tid; r < nn; r += T) mx = fmaxf(mx, nrm2[r]);
+    mx = block_max(mx, red_scratch);
+    const float zero_thr = 1e-14f * mx;
+    int rotated = 0;
+    for (int step = 0; step < ring; ++step) {
+      for (int base = 0; base < half; base += groups) {
+        const int pair = base + gid;
+        int p = 0, q = 0;
+        bool valid = pair < half;
+        if (valid) {
+          if (pair == 0) { p = ne - 1; q = step; }
+          else { p = step + pair; if (p >= ring) p -= ring; q = step - pair; if (q < 0) q += ring; }
+          valid = (p < nn) && (q < nn);
+        }
+        float4* rp = reinterpret_cast<float4*>(G + (long)p * ldw);
+        float4* rq = reinterpret_cast<float4*>(G + (long)q * ldw);
+        float4 x[NV], y[NV];
+        float ga = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int idx = gl + LP * v;
+          if (valid && idx < mv) {
+            x[v] = rp[idx];
+            y[v] = rq[idx];
+          } else {
+            x[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            y[v] = x[v];
+          }
+          ga = fmaf(x[v].x, y[v].x, ga); ga = fmaf(x[v].y, y[v].y, ga);
+          ga = fmaf(x[v].z, y[v].z, ga); ga = fmaf(x[v].w, y[v].w, ga);
+        }
+#pragma unroll
+        for (int o = LP >> 1; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        if (!valid) continue;
+        const float al = nrm2[p], be = nrm2[q];
+        if (!(ga * ga > tol2 * al * be) || al <= zero_thr || be <= zero_thr) continue;   // group-uniform
+        // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 ga), rewritten as
+        // t = sgn * 2|ga| / (|d| + sqrt(d^2 + 4 ga^2)) with d = be - al: one rsqrt, one divide.
+        const float d = be - al;
+        const float h = fmaf(d, d, 4.f * ga * ga);
+        const float root = h * rsqrtf(h);
+        float t = __fdividef(2.f * fabsf(ga), fabsf(d) + root);
+        t = ((d < 0.f) != (ga < 0.f)) ? -t : t;
+        const float w2 = fmaf(t, t, 1.f);
+        float c = rsqrtf(w2);
+        c = c * fmaf(-0.5f * w2, c * c, 1.5f);               // Newton: c^2 (1 + t^2) = 1 to an ulp
+        const float sn = c * t;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int idx = gl + LP * v;
+          if (idx < mv) {
+            const float4 a = x[v], b = y[v];
+            float4 na, nb;
+            na.x = fmaf(c, a.x, -sn * b.x); nb.x = fmaf(sn, a.x, c * b.x);
+            na.y = fmaf(c, a.y, -sn * b.y); nb.y = fmaf(sn, a.y, c * b.y);
+            na.z = fmaf(c, a.z, -sn * b.z); nb.z = fmaf(sn, a.z, c * b.z);
+            na.w = fmaf(c, a.w, -sn * b.w); nb.w = fmaf(sn, a.w, c * b.w);
+            rp[idx] = na;
+            rq[idx] = nb;
+          }
+        }
+        if (gl == 0) {
+          nrm2[p] = fmaxf(fmaf(-t, ga, al), 0.f);
+          nrm2[q] = fmaxf(fmaf(t, ga, be), 0.f);
+        }
+        rotated = 1;
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) { ++sweep; break; }
+  }
+  for (int e = tid; e < nn * mv; e += T) {
+    const int r = e / mv, c4 = (e - r * mv) * 4;
+    *reinterpret_cast<float4*>(Gg + (long)r * ld + c4) =
+        *reinterpret_cast<const float4*>(G + (long)r * ldw + c4);
+  }
+  if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
+}
+
 // ------------------------------------------------------------------ normalise (+ sort) rows
 // in:  G (n x m) whose rows are s_j * v_j^T ; out: Vt rows = v_j^T (zero if s_j <= floor),
 // vals[j] = s_j (square=0) or s_j^2 (square=1); sorted descending when sort != 0.
@@ -297,18 +449,30 @@ static int smem_limit() {
 template <int NV>
 static int launch_jacobi(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st) {
-  const size_t need = (size_t)n * (((size_t)m + 3) / 4 * 4) * sizeof(float);
-  const int use_smem = need + 1024 <= (size_t)smem_limit();
-  const size_t dyn = use_smem ? need : 0;
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_kernel<NV>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 0));
   int pairs = (n + 1) / 2;
   int threads = pairs * 32;
   const int cap = NV >= 3 ? 512 : 1024;
   if (threads > cap) threads = cap;
   if (threads < 64) threads = 64;
-  jacobi_rows_kernel<NV><<<batch, threads, dyn, st>>>(G, n, m, ld, stride, dims, tol, max_sweeps,
-                                                      use_smem, sweeps_out);
+  jacobi_rows_kernel<NV><<<batch, threads, 0, st>>>(G, n, m, ld, stride, dims, tol, max_sweeps, 0,
+                                                    sweeps_out);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int LP, int NV, int MAXT>
+static int launch_grouped(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                          float tol, int max_sweeps, int* sweeps_out, size_t dyn, cudaStream_t st) {
+  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_grouped_kernel<LP, NV, MAXT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int threads = ((n + 1) / 2) * LP;
+  threads = (threads + 31) / 32 * 32;
+  if (threads > MAXT) threads = MAXT / 32 * 32;
+  if (threads < 64) threads = 64;
+  jacobi_rows_grouped_kernel<LP, NV, MAXT><<<batch, threads, dyn, st>>>(
+      G, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out);
   BASD_LAUNCH_CHECK();
   return 0;
 }
@@ -321,8 +485,10 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
   using namespace basd;
   if (batch <= 0 || n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t base = (size_t)(2 * n + 128) * sizeof(float);
-  const size_t staged = base + (size_t)n * n * sizeof(float);
+  const size_t npad = ((size_t)n + 3) & ~(size_t)3;
+  const size_t base = (size_t)(2 * npad + 128) * sizeof(float);
+  const size_t staged = base + npad * npad * sizeof(float);
+  if (ld & 3) return -3;
   const int use_smem = staged + 1024 <= (size_t)smem_limit();
   const size_t dyn = use_smem ? staged : base;
   BASD_CUDA(cudaFuncSetAttribute(pivoted_cholesky_kernel,
@@ -344,6 +510,24 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
   if ((ld & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(G) & 15)) return -3;
   cudaStream_t st = (cudaStream_t)stream;
   const int quads = (m + 3) / 4;
+  // shared-memory resident path: LP lanes per pair
+  const size_t need = ((size_t)n * quads * 4 + n) * sizeof(float);
+  const bool legacy = getenv("BASD_JACOBI_LEGACY") != nullptr;   // A/B debugging aid
+  if (!legacy && need + 1024 <= (size_t)smem_limit()) {
+#define BASD_GROUPED(LP, NV, MAXT) \
+  return launch_grouped<LP, NV, MAXT>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, need, st)
+    if (quads <= 8) BASD_GROUPED(8, 1, 1024);
+    if (quads <= 16) BASD_GROUPED(8, 2, 1024);
+    if (quads <= 24) BASD_GROUPED(8, 3, 1024);
+    if (quads <= 32) BASD_GROUPED(8, 4, 1024);
+    if (quads <= 40) BASD_GROUPED(8, 5, 896);
+    if (quads <= 48) BASD_GROUPED(8, 6, 800);
+    if (quads <= 56) BASD_GROUPED(8, 7, 800);
+    if (quads <= 64) BASD_GROUPED(16, 4, 1024);
+    if (quads <= 96) BASD_GROUPED(16, 6, 832);
+    if (quads <= 128) BASD_GROUPED(32, 4, 1024);
+#undef BASD_GROUPED
+  }
   const int nv = (quads + 31) / 32;
   switch (nv) {
     case 1: return launch_jacobi<1>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
