@@ -13,7 +13,9 @@
 // row-Jacobi = Veselic-Hari), the k x k principal-angle SVDs (layer_selector.py:99) and the
 // per-sample Procrustes SVD (relational.py:48, reduced to N x N).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <cstdlib>
+namespace cg = cooperative_groups;
 
 namespace basd {
 
@@ -362,6 +364,122 @@ jacobi_rows_grouped_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
   if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
 }
 
+// Cluster variant for the few-but-large problems (projected-Gram eigenproblems, k x k
+// principal-angle SVDs: n up to 1024, a few dozen problems).  One thread-block CLUSTER per
+// problem: the matrix stays L2-resident in global memory, the n/2 independent row pairs of a
+// round-robin step are split over all warps of the cluster, and the step boundary is the
+// hardware cluster barrier (release/acquire at cluster scope) instead of a grid-wide sync.
+// Rows are read/written with L1-bypassing accesses so no SM ever sees a stale line.
+template <int NV, int R, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+jacobi_rows_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                           const int* __restrict__ dims, float tol, int max_sweeps,
+                           int* __restrict__ sweeps_out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = cluster.num_blocks(), crank = cluster.block_rank();
+  const int prob = blockIdx.x / csize;
+  __shared__ int flag;                                   // rank 0's copy is the cluster flag
+  int* flag0 = cluster.map_shared_rank(&flag, 0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int gwarp = crank * nwarps + warp, total_warps = csize * nwarps;
+  float* G = Gbase + (long)prob * stride;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
+  const int mv = (mm + 3) >> 2;
+  const int ne = nn + (nn & 1), ring = ne - 1, half = ne >> 1;
+  const float tol2 = tol * tol;
+  int sweep = 0;
+  for (; sweep < max_sweeps && nn >= 2; ++sweep) {
+    if (crank == 0 && tid == 0) flag = 0;
+    cluster.sync();
+    int rotated = 0;
+    for (int step = 0; step < ring; ++step) {
+      for (int base = 0; base < half; base += total_warps * R) {
+        float4 x[R][NV], y[R][NV];
+        int pp[R], qq[R];
+        bool ok[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                    // issue every load of this warp first
+          const int pair = base + gwarp + r * total_warps;
+          int p = 0, q = 0;
+          bool valid = pair < half;
+          if (valid) {
+            if (pair == 0) { p = ne - 1; q = step; }
+            else { p = step + pair; if (p >= ring) p -= ring; q = step - pair; if (q < 0) q += ring; }
+            valid = (p < nn) && (q < nn);
+          }
+          pp[r] = p; qq[r] = q; ok[r] = valid;
+          const float4* rp = reinterpret_cast<const float4*>(G + (long)p * ld);
+          const float4* rq = reinterpret_cast<const float4*>(G + (long)q * ld);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int idx = lane + 32 * v;
+            if (valid && idx < mv) {
+              x[r][v] = __ldcg(rp + idx);
+              y[r][v] = __ldcg(rq + idx);
+              const int c4 = idx * 4;                    // zero the tail past mm (dims < ld)
+              if (c4 + 1 >= mm) { x[r][v].y = 0.f; y[r][v].y = 0.f; }
+              if (c4 + 2 >= mm) { x[r][v].z = 0.f; y[r][v].z = 0.f; }
+              if (c4 + 3 >= mm) { x[r][v].w = 0.f; y[r][v].w = 0.f; }
+            } else {
+              x[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+              y[r][v] = x[r][v];
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const float4 a = x[r][v], b = y[r][v];
+            al = fmaf(a.x, a.x, al); al = fmaf(a.y, a.y, al); al = fmaf(a.z, a.z, al); al = fmaf(a.w, a.w, al);
+            be = fmaf(b.x, b.x, be); be = fmaf(b.y, b.y, be); be = fmaf(b.z, b.z, be); be = fmaf(b.w, b.w, be);
+            ga = fmaf(a.x, b.x, ga); ga = fmaf(a.y, b.y, ga); ga = fmaf(a.z, b.z, ga); ga = fmaf(a.w, b.w, ga);
+          }
+          al = warp_sum(al);
+          be = warp_sum(be);
+          ga = warp_sum(ga);
+          if (!ok[r] || !(ga * ga > tol2 * al * be)) continue;      // warp-uniform
+          const float d = be - al;
+          const float h = fmaf(d, d, 4.f * ga * ga);
+          const float root = h * rsqrtf(h);
+          float t = __fdividef(2.f * fabsf(ga), fabsf(d) + root);
+          t = ((d < 0.f) != (ga < 0.f)) ? -t : t;
+          const float w2 = fmaf(t, t, 1.f);
+          float c = rsqrtf(w2);
+          c = c * fmaf(-0.5f * w2, c * c, 1.5f);
+          const float sn = c * t;
+          float4* rp = reinterpret_cast<float4*>(G + (long)pp[r] * ld);
+          float4* rq = reinterpret_cast<float4*>(G + (long)qq[r] * ld);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int idx = lane + 32 * v;
+            if (idx < mv) {
+              const float4 a = x[r][v], b = y[r][v];
+              float4 na, nb;
+              na.x = fmaf(c, a.x, -sn * b.x); nb.x = fmaf(sn, a.x, c * b.x);
+              na.y = fmaf(c, a.y, -sn * b.y); nb.y = fmaf(sn, a.y, c * b.y);
+              na.z = fmaf(c, a.z, -sn * b.z); nb.z = fmaf(sn, a.z, c * b.z);
+              na.w = fmaf(c, a.w, -sn * b.w); nb.w = fmaf(sn, a.w, c * b.w);
+              __stcg(rp + idx, na);
+              __stcg(rq + idx, nb);
+            }
+          }
+          rotated = 1;
+        }
+      }
+      cluster.sync();                                    // step boundary for the whole cluster
+    }
+    if (__syncthreads_or(rotated) && tid == 0) atomicOr(flag0, 1);
+    cluster.sync();
+    const int any = *flag0;
+    cluster.sync();                                      // everyone has read before rank 0 resets
+    if (!any) { ++sweep; break; }
+  }
+  if (sweeps_out && crank == 0 && tid == 0) sweeps_out[prob] = sweep;
+}
+
 // ------------------------------------------------------------------ normalise (+ sort) rows
 // in:  G (n x m) whose rows are s_j * v_j^T ; out: Vt rows = v_j^T (zero if s_j <= floor),
 // vals[j] = s_j (square=0) or s_j^2 (square=1); sorted descending when sort != 0.
@@ -462,6 +580,40 @@ static int launch_jacobi(float* G, int n, int m, int ld, long stride, int batch,
   return 0;
 }
 
+static int sm_count() {
+  static int sms = -1;
+  if (sms < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+template <int NV, int R, int MAXT>
+static int launch_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st) {
+  int csize = 8;
+  while (csize > 1 && (long)batch * csize > sm_count()) csize >>= 1;
+  const int half = (n + 1) / 2;
+  while (csize > 1 && (csize / 2) * (MAXT / 32) * R >= half) csize >>= 1;   // no idle CTAs
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(batch * csize);
+  cfg.blockDim = dim3(MAXT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_cluster_kernel<NV, R, MAXT>, G, n, m, ld, stride,
+                               dims, tol, max_sweeps, sweeps_out));
+  return 0;
+}
+
 template <int LP, int NV, int MAXT>
 static int launch_grouped(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                           float tol, int max_sweeps, int* sweeps_out, size_t dyn, cudaStream_t st) {
@@ -529,6 +681,19 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
 #undef BASD_GROUPED
   }
   const int nv = (quads + 31) / 32;
+  if (!legacy) {
+    switch (nv) {
+      case 1: return launch_cluster<1, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+      case 2: return launch_cluster<2, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+      case 3: return launch_cluster<3, 2, 768>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+      case 4: return launch_cluster<4, 1, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+      case 5: case 6:
+        return launch_cluster<6, 1, 512>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+      case 7: case 8:
+        return launch_cluster<8, 1, 512>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+      default: return -4;
+    }
+  }
   switch (nv) {
     case 1: return launch_jacobi<1>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
     case 2: return launch_jacobi<2>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
