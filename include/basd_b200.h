@@ -48,6 +48,12 @@ long basd_token_gram_simt_workspace_floats(long rows, int D);
 int basd_token_gram_simt(const void* tokens, int dtype, long rows, int D, float* gram,
                          float* colsum, float* workspace, void* stream);
 
+/* Same statistic on the tensor cores (gram_tc.cu): TMA-fed tcgen05.mma (bf16 x bf16 -> fp32 in
+ * TMEM), 128x128 upper-triangular tiles, split-K over the token rows. bf16 tokens, D % 128 == 0. */
+long basd_token_gram_tc_workspace_bytes(long rows, int D);
+int basd_token_gram_tc(const void* tokens, long rows, int D, float* gram, float* colsum,
+                       void* workspace, void* stream);
+
 /* ---- small-matrix factorisations (jacobi.cu) ---------------------------------------- */
 
 /* Rank-revealing (diagonally pivoted) Cholesky of `batch` PSD matrices.  K is destroyed.

@@ -51,7 +51,8 @@ def test_sgemm_bf16_a_with_shift_and_shared_operand():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("rows,d", [(1024, 192), (4 * 196, 384), (3001, 200)])
+@pytest.mark.parametrize("rows,d", [(1024, 192), (4 * 196, 384), (3001, 200), (6272, 768), (1000, 256),
+                                    (50, 128)])
 def test_token_gram(dtype, rows, d):
     eng = _eng()
     torch.manual_seed(2)

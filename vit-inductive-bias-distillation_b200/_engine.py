@@ -45,7 +45,8 @@ def token_gram(tokens: torch.Tensor, gram: torch.Tensor, colsum: torch.Tensor):
     d = tokens.shape[-1]
     rows = tokens.numel() // d
     x = tokens if tokens.is_contiguous() else tokens.contiguous()
-    if x.dtype == torch.bfloat16 and nat.has("basd_token_gram_tc") and d % 64 == 0 and rows % 64 == 0:
+    if (x.dtype == torch.bfloat16 and nat.has("basd_token_gram_tc") and d % 128 == 0
+            and x.data_ptr() % 16 == 0):
         nbytes = nat.load().basd_token_gram_tc_workspace_bytes(rows, d)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         call("basd_token_gram_tc", ptr(x), rows, d, ptr(gram), ptr(colsum), ptr(ws), stream())

@@ -79,4 +79,10 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float out[8]) {
   }
 }
 
+// gemm_simt.cu helpers reused by gram_tc.cu
+int launch_gram_reduce(const float* partial, int slices, int D, int tile, float* gram,
+                       cudaStream_t st);
+int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial /* >= 64*D floats */,
+                       float* out, cudaStream_t st);
+
 }  // namespace basd

@@ -225,6 +225,30 @@ static int launch_sgemm(int a_dtype, int M, int N, int K, const void* A, int lda
   return 0;
 }
 
+// Host-side helpers shared with gram_tc.cu (declared in common.cuh).
+int launch_gram_reduce(const float* partial, int slices, int D, int tile, float* gram,
+                       cudaStream_t st) {
+  const long total = (long)D * D;
+  gram_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, slices, D, tile, gram,
+                                                                      0.f);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial, float* out,
+                       cudaStream_t st) {
+  int cs = (int)((rows + 4095) / 4096);
+  if (cs > 64) cs = 64;
+  if (cs < 1) cs = 1;
+  const long per = (rows + cs - 1) / cs;
+  dim3 cgrid((D + 31) / 32, cs);
+  colsum_partial_kernel<__nv_bfloat16><<<cgrid, 256, 0, st>>>((const __nv_bfloat16*)tokens, rows, D,
+                                                              per, partial);
+  colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(partial, cs, D, out);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace basd
 
 extern "C" int basd_sgemm_batched(int trans_a, int trans_b, int M, int N, int K, const void* A,
