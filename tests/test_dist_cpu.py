@@ -1,0 +1,91 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: sharded token statistics,
+packed and all-reduced exactly like `_engine.statistics` packs them, give the same MP ranks and
+mixing weights as one process on the concatenated batch.  Compute here is the CPU model (the
+CUDA kernels need a GPU) -- what is under test is the sharding contract: additive statistics,
+global row count, one flat buffer, shards that are slices of the global batch."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import basd_b200.synthetic as syn
+from oracle import kernel_model as km
+from tests import _cases as cs
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _pack(stats_s, stats_t):
+    parts = [torch.stack([g for g, _ in stats_s]).flatten(), torch.stack([c for _, c in stats_s]).flatten(),
+             torch.stack([g for g, _ in stats_t]).flatten(), torch.stack([c for _, c in stats_t]).flatten()]
+    return torch.cat(parts), [p.numel() for p in parts]
+
+
+def _unpack(flat, sizes, e, l, d_s, d_t):
+    a, b, c, d = torch.split(flat, sizes)
+    return (list(zip(a.view(e, d_s, d_s), b.view(e, d_s))), list(zip(c.view(l, d_t, d_t), d.view(l, d_t))))
+
+
+def _worker(rank, world, port, local_batch, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from basd_b200 import _autograd, _engine
+        assert _autograd.world_size(None) == world
+        work = cs.workload("c1", local_batch)
+        _, _, st, te, _ = syn.make_inputs(work, seed=4, batch_offset=rank * local_batch)
+        layers = sorted(st)
+        flat, sizes = _pack([km.token_stats(st[l]) for l in layers],
+                            [km.token_stats(te[k]) for k in sorted(te)])
+        _engine._all_reduce(flat, None)                       # the product's collective helper
+        stats_s, stats_t = _unpack(flat, sizes, len(layers), len(te), work.d_student, work.d_teacher)
+        proj_s, proj_t, logt = cs.selector_state(work)
+        rows = world * local_batch * work.n_student
+        sel = km.selector_model(stats_s, stats_t, rows, rows, proj_s, proj_t, logt)
+        if rank == 0:
+            out.put((sel["ranks"], torch.stack(sel["weights"]).tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_statistics_equal_concatenated_batch():
+    world, local_batch = 2, 8
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, local_batch, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ranks, weights = out.get()
+    weights = torch.tensor(weights)
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    work = cs.workload("c1", world * local_batch)
+    _, _, st, te, _ = syn.make_inputs(work, seed=4)
+    layers = sorted(st)
+    proj_s, proj_t, logt = cs.selector_state(work)
+    rows = work.batch * work.n_student
+    ref = km.selector_model([km.token_stats(st[l]) for l in layers], [km.token_stats(te[k]) for k in sorted(te)],
+                            rows, rows, proj_s, proj_t, logt)
+    assert ranks == ref["ranks"]
+    assert (weights - torch.stack(ref["weights"])).abs().max() < 1e-5
+
+
+def test_shards_are_slices_of_the_global_batch():
+    work8, work16 = cs.workload("c1", 8), cs.workload("c1", 16)
+    full = syn.make_inputs(work16, seed=4)
+    lo = syn.make_inputs(work8, seed=4, batch_offset=0)
+    hi = syn.make_inputs(work8, seed=4, batch_offset=8)
+    for k in full[2]:
+        assert torch.equal(torch.cat([lo[2][k], hi[2][k]]), full[2][k])
+    for k in full[3]:
+        assert torch.equal(torch.cat([lo[3][k], hi[3][k]]), full[3][k])
+        assert torch.equal(torch.cat([lo[4][k], hi[4][k]]), full[4][k])
+    assert torch.equal(torch.cat([lo[1], hi[1]]), full[1])

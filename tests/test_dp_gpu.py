@@ -1,0 +1,20 @@
+"""N-GPU data-parallel parity (needs >= 2 GPUs on the box; skipped otherwise)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_two_rank_loss_equals_concatenated_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tools", "dp_parity.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(res.stdout[-3000:], res.stderr[-2000:])
+    assert res.returncode == 0

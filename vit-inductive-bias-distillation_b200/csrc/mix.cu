@@ -49,7 +49,7 @@ __global__ void attn_rows_kernel(const T* __restrict__ attn, int H, int side, in
 }
 
 // One thread per (b, n_dst, 8-wide column group). VEC = 8 elements.
-template <typename TIn, typename TOut>
+template <typename TIn, typename TOut, int NE>
 __global__ void __launch_bounds__(256)
 mix_interp_kernel(LayerPtrs layers, int L, int E, const float* __restrict__ weights, int B,
                   int n_src, int n_dst, int D, TOut* __restrict__ out) {
@@ -67,49 +67,67 @@ mix_interp_kernel(LayerPtrs layers, int L, int E, const float* __restrict__ weig
   int lo, hi;
   float f;
   taps(n, n_src, n_dst, lo, hi, f);
-  float acc[MAX_E][8];
+  float acc[NE][8];
 #pragma unroll
-  for (int i = 0; i < MAX_E; ++i)
+  for (int i = 0; i < NE; ++i)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
   const long off_lo = ((long)b * n_src + lo) * D + g * 8;
   const long off_hi = ((long)b * n_src + hi) * D + g * 8;
-  for (int l = 0; l < L; ++l) {
-    const TIn* src = reinterpret_cast<const TIn*>(layers.p[l]);
-    float v[8];
-    if (sizeof(TIn) == 2) {
-      load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_lo, v);
-      if (f != 0.f) {
-        float u[8];
-        load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_hi, u);
+  // layers are walked four at a time with every 128-bit load of the group issued before any
+  // of them is consumed: 4-8 independent requests in flight per thread (HBM latency hiding)
+  constexpr int UNR = 4;
+  for (int l0 = 0; l0 < L; l0 += UNR) {
+    float v[UNR][8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = fmaf(f, u[c] - v[c], v[c]);
+    for (int u = 0; u < UNR; ++u) {
+      const int l = min(l0 + u, L - 1);
+      const TIn* src = reinterpret_cast<const TIn*>(layers.p[l]);
+      if (sizeof(TIn) == 2) {
+        load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_lo, v[u]);
+      } else {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off_lo);
+        const float4 a = __ldg(p), bq = __ldg(p + 1);
+        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+        v[u][4] = bq.x; v[u][5] = bq.y; v[u][6] = bq.z; v[u][7] = bq.w;
       }
-    } else {
-      const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off_lo);
-      const float4 a = __ldg(p), bq = __ldg(p + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
-      if (f != 0.f) {
-        const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off_hi);
-        const float4 c0 = __ldg(q), c1 = __ldg(q + 1);
-        const float u[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    }
+    if (f != 0.f) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = fmaf(f, u[c] - v[c], v[c]);
+      for (int u = 0; u < UNR; ++u) {
+        const int l = min(l0 + u, L - 1);
+        const TIn* src = reinterpret_cast<const TIn*>(layers.p[l]);
+        float hv[8];
+        if (sizeof(TIn) == 2) {
+          load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_hi, hv);
+        } else {
+          const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off_hi);
+          const float4 c0 = __ldg(q), c1 = __ldg(q + 1);
+          hv[0] = c0.x; hv[1] = c0.y; hv[2] = c0.z; hv[3] = c0.w;
+          hv[4] = c1.x; hv[5] = c1.y; hv[6] = c1.z; hv[7] = c1.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[u][c] = fmaf(f, hv[c] - v[u][c], v[u][c]);
       }
     }
 #pragma unroll
-    for (int i = 0; i < MAX_E; ++i) {
-      if (i < E) {
-        const float wi = w[i * L + l];
+    for (int u = 0; u < UNR; ++u) {
+      if (l0 + u < L) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(wi, v[c], acc[i][c]);
+        for (int i = 0; i < NE; ++i) {
+          if (i < E) {
+            const float wi = w[i * L + l0 + u];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(wi, v[u][c], acc[i][c]);
+          }
+        }
       }
     }
   }
   const long slab = (long)B * n_dst * D;
   const long o = ((long)b * n_dst + n) * D + g * 8;
 #pragma unroll
-  for (int i = 0; i < MAX_E; ++i) {
+  for (int i = 0; i < NE; ++i) {
     if (i < E) {
       TOut* dst = out + (long)i * slab + o;
       if (sizeof(TOut) == 2) {
@@ -283,17 +301,25 @@ extern "C" int basd_mix_interp(const void* const* teacher_layers, int L, int E, 
   if (int rc = fill_layers(lp, teacher_layers, L)) return rc;
   const long total = (long)B * n_dst * (D >> 3);
   const unsigned grid = (unsigned)((total + 255) / 256);
+#define BASD_MIX(TI, TO, NE) \
+  mix_interp_kernel<TI, TO, NE><<<grid, 256, 0, ST>>>(lp, L, E, weights, B, n_src, n_dst, D, (TO*)out)
+#define BASD_MIX_E(TI, TO)              \
+  do {                                  \
+    if (E <= 1) BASD_MIX(TI, TO, 1);    \
+    else if (E <= 2) BASD_MIX(TI, TO, 2); \
+    else if (E <= 4) BASD_MIX(TI, TO, 4); \
+    else BASD_MIX(TI, TO, 8);           \
+  } while (0)
   if (in_dtype == BASD_DTYPE_BF16 && out_dtype == BASD_DTYPE_BF16)
-    mix_interp_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, ST>>>(
-        lp, L, E, weights, B, n_src, n_dst, D, (__nv_bfloat16*)out);
+    BASD_MIX_E(__nv_bfloat16, __nv_bfloat16);
   else if (in_dtype == BASD_DTYPE_BF16)
-    mix_interp_kernel<__nv_bfloat16, float><<<grid, 256, 0, ST>>>(lp, L, E, weights, B, n_src, n_dst,
-                                                                  D, (float*)out);
+    BASD_MIX_E(__nv_bfloat16, float);
   else if (out_dtype == BASD_DTYPE_F32)
-    mix_interp_kernel<float, float><<<grid, 256, 0, ST>>>(lp, L, E, weights, B, n_src, n_dst, D,
-                                                          (float*)out);
+    BASD_MIX_E(float, float);
   else
     return -8;
+#undef BASD_MIX_E
+#undef BASD_MIX
   BASD_LAUNCH_CHECK();
   return 0;
 }
