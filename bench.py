@@ -19,6 +19,7 @@ import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -150,7 +151,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     work = syn.scaled(syn.WORKLOADS[args.workload], args.batch)
     mod = build_module(work, device)
     logits, targets, st, te, at = syn.make_inputs_fast(work, seed=rank, device=device)
@@ -240,8 +242,9 @@ def run_b200(args):
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 4, "ms_per_step": round(float(t.item()), 3)},
     }
+    # every rank runs the profiled step (the loss all-reduces inside); only rank 0 reports
+    records, total, fp32_peak = roofline(work, mod, args5, pk, clocks)
     if rank == 0:
-        records, total, fp32_peak = roofline(work, mod, args5, pk, clocks)
         line["kernels"] = records[:12]
         line["kernel_ms_total"] = round(total, 3)
         top = next((r for r in records if "achieved" in r), None)
