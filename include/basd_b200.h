@@ -113,10 +113,11 @@ int basd_symmetrize_add(const float* in, int D, float* out, int batch, void* str
 
 /* ---- HBM-bound mixing (mix.cu) ------------------------------------------------------ */
 
-/* attention map (B,H,side,side) -> importance row (B, n_tok): CLS row mean over heads, or
- * mean over (heads, queries) without CLS.                      (relational.py:22-27) */
-int basd_attn_rows(const void* attn, int dtype, int B, int H, int side, int has_cls, float* rows,
-                   void* stream);
+/* attention map (B,H,q_rows,side) -> importance row (B, n_tok): CLS row mean over heads, or
+ * mean over (heads, queries) without CLS.  q_rows = side for a full map, 1 when the caller
+ * hands over only the CLS query row.                           (relational.py:22-27) */
+int basd_attn_rows(const void* attn, int dtype, int B, int H, int side, int q_rows, int has_cls,
+                   float* rows, void* stream);
 
 /* out[i] = resample_{n_src->n_dst}( sum_l weights[i,l] * teacher_l ), all i in one pass.
  * teacher_layers: HOST array of L device pointers, each (B, n_src, D).

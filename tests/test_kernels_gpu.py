@@ -147,7 +147,7 @@ def test_attn_rows(has_cls, dtype):
     attn = torch.softmax(torch.randn(b, h, side, side, device=DEV), -1).to(dtype)
     n_tok = side - 1 if has_cls else side
     rows = torch.empty(b, n_tok, device=DEV)
-    call("basd_attn_rows", ptr(attn), dtype_code(attn), b, h, side, int(has_cls), ptr(rows), stream())
+    call("basd_attn_rows", ptr(attn), dtype_code(attn), b, h, side, side, int(has_cls), ptr(rows), stream())
     a = attn.float()
     ref = a[:, :, 0, 1:].mean(1) if has_cls else a.mean((1, 2))
     assert (rows - ref).abs().max() < 1e-6

@@ -136,9 +136,13 @@ def statistics(students, teachers, attns, has_cls):
         if a.dim() == 2:      # already an importance row (B, Nt): "next" row f1 of SURVEY §8
             rows[j].copy_(a)
             continue
-        _, h, side, _ = a.shape
-        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, int(has_cls), ptr(rows[j]),
-             stream())
+        if a.dim() == 3:      # (B, H, side): only the CLS query row was handed over
+            _, h, side = a.shape
+            q_rows = 1
+        else:
+            _, h, q_rows, side = a.shape
+        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, q_rows, int(has_cls),
+             ptr(rows[j]), stream())
     return Stats(gram_s, col_s, gram_t, col_t, rows), flat
 
 
@@ -153,9 +157,13 @@ def attention_only_stats(teachers, attns, has_cls):
         if a.dim() == 2:
             rows[j].copy_(a)
             continue
-        _, h, side, _ = a.shape
-        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, int(has_cls), ptr(rows[j]),
-             stream())
+        if a.dim() == 3:      # (B, H, side): only the CLS query row was handed over
+            _, h, side = a.shape
+            q_rows = 1
+        else:
+            _, h, q_rows, side = a.shape
+        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, q_rows, int(has_cls),
+             ptr(rows[j]), stream())
     return Stats(None, None, None, None, rows)
 
 

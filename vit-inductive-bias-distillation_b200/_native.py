@@ -38,7 +38,7 @@ _SIG = {
     "basd_scale_rows_dsigma": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "basd_omega_accumulate": [_p, _p, _p, _i, _i, _i, _p, _p],
     "basd_symmetrize_add": [_p, _i, _p, _i, _p],
-    "basd_attn_rows": [_p, _i, _i, _i, _i, _i, _p, _p],
+    "basd_attn_rows": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "basd_mix_interp": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p],
     "basd_mix_rows": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "basd_weight_grad_slices": [],

@@ -14,20 +14,51 @@ namespace basd {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
-template <bool TA, bool TB, typename AT>
-__global__ void __launch_bounds__(256)
+// Loads up to 4 consecutive elements (fewer when `remaining` < 4) as floats.
+template <typename T>
+__device__ __forceinline__ void load_quad(const T* __restrict__ src, int remaining, bool vec,
+                                          float v[4]);
+template <>
+__device__ __forceinline__ void load_quad<float>(const float* __restrict__ src, int remaining,
+                                                 bool vec, float v[4]) {
+  if (vec && remaining >= 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (i < remaining) ? src[i] : 0.f;
+  }
+}
+template <>
+__device__ __forceinline__ void load_quad<__nv_bfloat16>(const __nv_bfloat16* __restrict__ src,
+                                                         int remaining, bool vec, float v[4]) {
+  if (vec && remaining >= 4) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(src));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (i < remaining) ? __bfloat162float(src[i]) : 0.f;
+  }
+}
+
+// Tile shape is a template parameter: 64 or 68 rows/columns.  The per-sample matrices of the
+// C2-C4 workloads have 196 rows (3 x 68 = 204 wastes 4 %; 4 x 64 = 256 wasted 31 %).
+template <bool TA, bool TB, typename AT, int TM, int TN>
+__global__ void __launch_bounds__((TM / 4) * (TN / 4))
 sgemm_kernel(int M, int N, int K, const AT* __restrict__ A, int lda, long sA,
              const float* __restrict__ a_shift, const float* __restrict__ B, int ldb, long sB,
              float* __restrict__ C, int ldc, long sC, float alpha,
-             const float* __restrict__ alpha_dev, float beta) {
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+             const float* __restrict__ alpha_dev, float beta, bool vec) {
+  constexpr int NT = (TM / 4) * (TN / 4), TXN = TN / 4;
+  __shared__ __align__(16) float As[BK][TM + 4];
+  __shared__ __align__(16) float Bs[BK][TN + 4];
   const int batch = blockIdx.z;
   A += (long)batch * sA;
   B += (long)batch * sB;
   C += (long)batch * sC;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -35,43 +66,47 @@ sgemm_kernel(int M, int N, int K, const AT* __restrict__ A, int lda, long sA,
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   for (int k0 = 0; k0 < K; k0 += BK) {
-    if (!TA) {  // A[m][k], k contiguous
-      const int m = tid >> 2, kk = (tid & 3) * 4;
-      const bool row_ok = (m0 + m) < M;
-      const AT* src = A + (long)(m0 + m) * lda + k0 + kk;
+    // Tiles are filled in quads of 4 elements along the operand's contiguous dimension
+    // (one 128-bit / 64-bit global load when the quad is aligned and in range).
+    if (!TA) {  // A[m][k], k contiguous: TM rows x 4 quads
+      for (int q = tid; q < TM * 4; q += NT) {
+        const int m = q >> 2, kk = (q & 3) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if ((m0 + m) < M) {
+          const AT* src = A + (long)(m0 + m) * lda + k0 + kk;
+          load_quad<AT>(src, K - (k0 + kk), vec, v);
+          if (a_shift) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = k0 + kk + i;
-        float v = 0.f;
-        if (row_ok && k < K) {
-          v = to_f32<AT>(src[i]);
-          if (a_shift) v -= a_shift[k];
+            for (int i = 0; i < 4; ++i)
+              if (k0 + kk + i < K) v[i] -= a_shift[k0 + kk + i];
+          }
         }
-        As[kk + i][m] = v;
-      }
-    } else {  // A stored [k][m], m contiguous
-      const int kk = tid >> 4, mm = (tid & 15) * 4;
-      const bool k_ok = (k0 + kk) < K;
-      const AT* src = A + (long)(k0 + kk) * lda + m0 + mm;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float v = 0.f;
-        if (k_ok && (m0 + mm + i) < M) v = to_f32<AT>(src[i]);
-        As[kk][mm + i] = v;
+        for (int i = 0; i < 4; ++i) As[kk + i][m] = v[i];
+      }
+    } else {  // A stored [k][m], m contiguous: BK rows x TM/4 quads
+      for (int q = tid; q < BK * (TM / 4); q += NT) {
+        const int kk = q / (TM / 4), mm = (q % (TM / 4)) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if ((k0 + kk) < K) load_quad<AT>(A + (long)(k0 + kk) * lda + m0 + mm, M - (m0 + mm), vec, v);
+        *reinterpret_cast<float4*>(&As[kk][mm]) = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
     if (!TB) {  // B[k][n], n contiguous
-      const int kk = tid >> 4, nn = (tid & 15) * 4;
-      const bool k_ok = (k0 + kk) < K;
-      const float* src = B + (long)(k0 + kk) * ldb + n0 + nn;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) Bs[kk][nn + i] = (k_ok && (n0 + nn + i) < N) ? src[i] : 0.f;
+      for (int q = tid; q < BK * (TN / 4); q += NT) {
+        const int kk = q / (TN / 4), nn = (q % (TN / 4)) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if ((k0 + kk) < K) load_quad<float>(B + (long)(k0 + kk) * ldb + n0 + nn, N - (n0 + nn), vec, v);
+        *reinterpret_cast<float4*>(&Bs[kk][nn]) = make_float4(v[0], v[1], v[2], v[3]);
+      }
     } else {  // B stored [n][k], k contiguous
-      const int n = tid >> 2, kk = (tid & 3) * 4;
-      const bool col_ok = (n0 + n) < N;
-      const float* src = B + (long)(n0 + n) * ldb + k0 + kk;
+      for (int q = tid; q < TN * 4; q += NT) {
+        const int n = q >> 2, kk = (q & 3) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if ((n0 + n) < N) load_quad<float>(B + (long)(n0 + n) * ldb + k0 + kk, K - (k0 + kk), vec, v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) Bs[kk + i][n] = (col_ok && (k0 + kk + i) < K) ? src[i] : 0.f;
+        for (int i = 0; i < 4; ++i) Bs[kk + i][n] = v[i];
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -207,22 +242,50 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ partial, int slic
   out[d] = s;
 }
 
+static inline int pick_tile(int extent) {
+  const int w64 = (extent + 63) / 64 * 64, w68 = (extent + 67) / 68 * 68;
+  return w68 < w64 ? 68 : 64;
+}
+
+template <bool TA, bool TB, typename AT, int TM, int TN>
+static int launch_sgemm_tile(int M, int N, int K, const void* A, int lda, long sA,
+                             const float* a_shift, const float* B, int ldb, long sB, float* C,
+                             int ldc, long sC, int batch, float alpha, const float* alpha_dev,
+                             float beta, cudaStream_t st) {
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, batch);
+  // 128-bit operand loads need 4-element pitches/strides and 16-byte aligned bases
+  const bool vec = !(lda & 3) && !(ldb & 3) && !(sA & 3) && !(sB & 3) &&
+                   !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(B) & 15);
+  sgemm_kernel<TA, TB, AT, TM, TN><<<grid, (TM / 4) * (TN / 4), 0, st>>>(
+      M, N, K, (const AT*)A, lda, sA, a_shift, B, ldb, sB, C, ldc, sC, alpha, alpha_dev, beta, vec);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool TA, bool TB, typename AT>
+static int launch_sgemm_type(int M, int N, int K, const void* A, int lda, long sA,
+                             const float* a_shift, const float* B, int ldb, long sB, float* C,
+                             int ldc, long sC, int batch, float alpha, const float* alpha_dev,
+                             float beta, cudaStream_t st) {
+  const int tm = pick_tile(M), tn = pick_tile(N);
+#define BASD_ARGS M, N, K, A, lda, sA, a_shift, B, ldb, sB, C, ldc, sC, batch, alpha, alpha_dev, beta, st
+  if (tm == 68 && tn == 68) return launch_sgemm_tile<TA, TB, AT, 68, 68>(BASD_ARGS);
+  if (tm == 68) return launch_sgemm_tile<TA, TB, AT, 68, 64>(BASD_ARGS);
+  if (tn == 68) return launch_sgemm_tile<TA, TB, AT, 64, 68>(BASD_ARGS);
+  return launch_sgemm_tile<TA, TB, AT, 64, 64>(BASD_ARGS);
+#undef BASD_ARGS
+}
+
 template <bool TA, bool TB>
 static int launch_sgemm(int a_dtype, int M, int N, int K, const void* A, int lda, long sA,
                         const float* a_shift, const float* B, int ldb, long sB, float* C, int ldc,
                         long sC, int batch, float alpha, const float* alpha_dev, float beta,
                         cudaStream_t st) {
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, batch);
   if (a_dtype == BASD_DTYPE_BF16)
-    sgemm_kernel<TA, TB, __nv_bfloat16><<<grid, 256, 0, st>>>(
-        M, N, K, (const __nv_bfloat16*)A, lda, sA, a_shift, B, ldb, sB, C, ldc, sC, alpha,
-        alpha_dev, beta);
-  else
-    sgemm_kernel<TA, TB, float><<<grid, 256, 0, st>>>(M, N, K, (const float*)A, lda, sA, a_shift,
-                                                      B, ldb, sB, C, ldc, sC, alpha, alpha_dev,
-                                                      beta);
-  BASD_LAUNCH_CHECK();
-  return 0;
+    return launch_sgemm_type<TA, TB, __nv_bfloat16>(M, N, K, A, lda, sA, a_shift, B, ldb, sB, C, ldc,
+                                                    sC, batch, alpha, alpha_dev, beta, st);
+  return launch_sgemm_type<TA, TB, float>(M, N, K, A, lda, sA, a_shift, B, ldb, sB, C, ldc, sC, batch,
+                                          alpha, alpha_dev, beta, st);
 }
 
 // Host-side helpers shared with gram_tc.cu (declared in common.cuh).

@@ -28,85 +28,84 @@ __global__ void pivoted_cholesky_kernel(float* __restrict__ Kbase, int n, int ld
                                         float rel_tol, int* __restrict__ rank_out,
                                         const int* __restrict__ dims, int use_smem) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ unsigned long long best_key[2];   // (pivot value bits << 32) | ~index, double-buffered
   const int prob = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
   float* Kg = Kbase + (long)prob * strideK;
   float* LT = LTbase + (long)prob * strideL;
   const int nn = dims ? min(dims[prob], n) : n;
   const int npad = (n + 3) & ~3;
   float* colv = smem;                // npad (zero beyond nn)
-  float* diag = colv + npad;         // npad
-  float* red = diag + npad;          // 64
-  int* redi = reinterpret_cast<int*>(red + 64);  // 64
-  float* As = red + 128;             // npad*npad when staged
+  float* diag = colv + npad;         // npad: remaining pivot candidates, -1 once eliminated
+  float* red = diag + npad;          // 32
+  float* As = red + 32;              // npad*npad when staged
   float* A = use_smem ? As : Kg;
   const int lda = use_smem ? ((nn + 3) & ~3) : ld;
   if (use_smem) {
-    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     for (int r = warp; r < nn; r += nwarp)
       for (int c = lane; c < lda; c += 32) As[r * lda + c] = (c < nn) ? Kg[(long)r * ld + c] : 0.f;
   }
   for (int i = tid; i < npad; i += T) colv[i] = 0.f;
+  if (tid < 2) best_key[tid] = 0ull;
   __syncthreads();
+  auto pack = [](float v, int i) -> unsigned long long {
+    return (static_cast<unsigned long long>(__float_as_uint(fmaxf(v, 0.f))) << 32) |
+           static_cast<unsigned long long>(0xffffffffu - static_cast<unsigned>(i));
+  };
   float dmax = 0.f;
-  for (int i = tid; i < nn; i += T) {
-    const float d = A[(long)i * lda + i];
-    diag[i] = d;
-    dmax = fmaxf(dmax, d);
+  {
+    unsigned long long mine = 0ull;
+    for (int i = tid; i < nn; i += T) {
+      const float d = A[(long)i * lda + i];
+      diag[i] = d;
+      dmax = fmaxf(dmax, d);
+      const unsigned long long k = pack(d, i);
+      mine = k > mine ? k : mine;
+    }
+    if (mine) atomicMax(&best_key[0], mine);
   }
   dmax = block_max(dmax, red);
   const float floor_v = rel_tol * dmax;
   __syncthreads();
   int rank = 0;
   for (int j = 0; j < nn; ++j) {
-    // ---- block argmax of the remaining diagonal (eliminated entries hold -1)
-    float best = -1.f;
-    int arg = 0;
-    for (int i = tid; i < nn; i += T) {
-      const float d = diag[i];
-      if (d > best) { best = d; arg = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-    }
-    if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = arg; }
-    __syncthreads();
-    const int nw = (T + 31) >> 5;
-    best = red[0];
-    arg = redi[0];
-    for (int w = 1; w < nw; ++w)
-      if (red[w] > best || (red[w] == best && redi[w] < arg)) { best = red[w]; arg = redi[w]; }
-    if (!(best > floor_v) || !(best > 0.f)) break;   // uniform across the block
+    const unsigned long long key = best_key[j & 1];
+    const float best = __uint_as_float(static_cast<unsigned>(key >> 32));
+    const int p = static_cast<int>(0xffffffffu - static_cast<unsigned>(key & 0xffffffffu));
+    if (!(best > floor_v) || !(best > 0.f)) break;           // uniform across the block
     const float rs = rsqrtf(best);
-    const int p = arg;
-    for (int i = tid; i < nn; i += T) {
+    for (int i = tid; i < nn; i += T) {                      // column j of L = row p of the Schur complement
       float c = (diag[i] < 0.f) ? 0.f : A[(long)p * lda + i] * rs;
       if (i == p) c = best * rs;
       colv[i] = c;
       LT[(long)j * ldl + i] = c;
     }
+    if (tid == 0) best_key[(j + 1) & 1] = 0ull;
     __syncthreads();
-    {   // rank-1 update A -= col col^T, one warp per row, 128-bit column chunks
-      const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
-      const int quads = lda >> 2;                 // lda % 4 == 0 on both paths
+    {   // rank-1 update (one warp per row, 128-bit chunks) fused with the next pivot search
+      const int quads = lda >> 2;
+      unsigned long long mine = 0ull;
       for (int i = warp; i < nn; i += nwarp) {
+        const float di = diag[i];
+        if (di < 0.f) continue;                              // already eliminated
         const float ci = colv[i];
-        if (ci == 0.f) continue;                  // eliminated row: nothing to do
-        float4* row = reinterpret_cast<float4*>(A + (long)i * lda);
-        for (int k4 = lane; k4 < quads; k4 += 32) {
-          const float4 ck = *reinterpret_cast<const float4*>(colv + 4 * k4);
-          float4 a = row[k4];
-          a.x = fmaf(-ci, ck.x, a.x); a.y = fmaf(-ci, ck.y, a.y);
-          a.z = fmaf(-ci, ck.z, a.z); a.w = fmaf(-ci, ck.w, a.w);
-          row[k4] = a;
+        if (i == p) { if (lane == 0) diag[i] = -1.f; continue; }
+        if (ci != 0.f) {
+          float4* row = reinterpret_cast<float4*>(A + (long)i * lda);
+          for (int k4 = lane; k4 < quads; k4 += 32) {
+            const float4 ck = *reinterpret_cast<const float4*>(colv + 4 * k4);
+            float4 a = row[k4];
+            a.x = fmaf(-ci, ck.x, a.x); a.y = fmaf(-ci, ck.y, a.y);
+            a.z = fmaf(-ci, ck.z, a.z); a.w = fmaf(-ci, ck.w, a.w);
+            row[k4] = a;
+          }
         }
+        const float nd = fmaxf(fmaf(-ci, ci, di), 0.f);
+        if (lane == 0) diag[i] = nd;
+        const unsigned long long k = pack(nd, i);
+        mine = k > mine ? k : mine;
       }
-    }
-    for (int i = tid; i < nn; i += T) {
-      if (i == p) diag[i] = -1.f;
-      else if (diag[i] >= 0.f) diag[i] = fmaxf(diag[i] - colv[i] * colv[i], 0.f);
+      if (lane == 0 && mine) atomicMax(&best_key[(j + 1) & 1], mine);
     }
     __syncthreads();
     rank = j + 1;
@@ -288,7 +287,7 @@ jacobi_rows_grouped_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
     for (int r = tid; r < nn; r += T) mx = fmaxf(mx, nrm2[r]);
     mx = block_max(mx, red_scratch);
     const float zero_thr = 1e-14f * mx;
-    int rotated = 0;
+    float worst = 0.f;        // largest cos^2 between two rows met in this sweep (before rotating)
     for (int step = 0; step < ring; ++step) {
       for (int base = 0; base < half; base += groups) {
         const int pair = base + gid;
@@ -321,6 +320,7 @@ jacobi_rows_grouped_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
         if (!valid) continue;
         const float al = nrm2[p], be = nrm2[q];
         if (!(ga * ga > tol2 * al * be) || al <= zero_thr || be <= zero_thr) continue;   // group-uniform
+        worst = fmaxf(worst, __fdividef(ga * ga, al * be));
         // t = sgn(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 ga), rewritten as
         // t = sgn * 2|ga| / (|d| + sqrt(d^2 + 4 ga^2)) with d = be - al: one rsqrt, one divide.
         const float d = be - al;
@@ -350,11 +350,14 @@ jacobi_rows_grouped_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
           nrm2[p] = fmaxf(fmaf(-t, ga, al), 0.f);
           nrm2[q] = fmaxf(fmaf(t, ga, be), 0.f);
         }
-        rotated = 1;
       }
       __syncthreads();
     }
-    if (!__syncthreads_or(rotated)) { ++sweep; break; }
+    // Jacobi converges quadratically: once every |cos| met in a sweep is below sqrt(tol), the
+    // rows are orthogonal to ~tol after it -- no separate verification sweep is needed.
+    worst = block_max(worst, red_scratch);
+    if (worst < tol) { ++sweep; break; }
+    __syncthreads();
   }
   for (int e = tid; e < nn * mv; e += T) {
     const int r = e / mv, c4 = (e - r * mv) * 4;
@@ -379,6 +382,7 @@ jacobi_rows_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
   const int csize = cluster.num_blocks(), crank = cluster.block_rank();
   const int prob = blockIdx.x / csize;
   __shared__ int flag;                                   // rank 0's copy is the cluster flag
+  __shared__ float red_scratch[32];
   int* flag0 = cluster.map_shared_rank(&flag, 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int gwarp = crank * nwarps + warp, total_warps = csize * nwarps;
@@ -392,7 +396,7 @@ jacobi_rows_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
   for (; sweep < max_sweeps && nn >= 2; ++sweep) {
     if (crank == 0 && tid == 0) flag = 0;
     cluster.sync();
-    int rotated = 0;
+    float worst = 0.f;
     for (int step = 0; step < ring; ++step) {
       for (int base = 0; base < half; base += total_warps * R) {
         float4 x[R][NV], y[R][NV];
@@ -441,6 +445,7 @@ jacobi_rows_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
           be = warp_sum(be);
           ga = warp_sum(ga);
           if (!ok[r] || !(ga * ga > tol2 * al * be)) continue;      // warp-uniform
+          worst = fmaxf(worst, __fdividef(ga * ga, al * be));
           const float d = be - al;
           const float h = fmaf(d, d, 4.f * ga * ga);
           const float root = h * rsqrtf(h);
@@ -466,16 +471,17 @@ jacobi_rows_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
               __stcg(rq + idx, nb);
             }
           }
-          rotated = 1;
         }
       }
       cluster.sync();                                    // step boundary for the whole cluster
     }
-    if (__syncthreads_or(rotated) && tid == 0) atomicOr(flag0, 1);
+    // cluster-wide max of cos^2 (non-negative floats order like their bit patterns)
+    worst = block_max(worst, red_scratch);
+    if (tid == 0) atomicMax(flag0, __float_as_int(worst));
     cluster.sync();
-    const int any = *flag0;
+    const float all_worst = __int_as_float(*flag0);
     cluster.sync();                                      // everyone has read before rank 0 resets
-    if (!any) { ++sweep; break; }
+    if (all_worst < tol) { ++sweep; break; }             // quadratic convergence: see grouped kernel
   }
   if (sweeps_out && crank == 0 && tid == 0) sweeps_out[prob] = sweep;
 }
@@ -638,14 +644,14 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
   if (batch <= 0 || n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t npad = ((size_t)n + 3) & ~(size_t)3;
-  const size_t base = (size_t)(2 * npad + 128) * sizeof(float);
+  const size_t base = (size_t)(2 * npad + 32) * sizeof(float);
   const size_t staged = base + npad * npad * sizeof(float);
   if (ld & 3) return -3;
   const int use_smem = staged + 1024 <= (size_t)smem_limit();
   const size_t dyn = use_smem ? staged : base;
   BASD_CUDA(cudaFuncSetAttribute(pivoted_cholesky_kernel,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  int threads = n >= 128 ? 1024 : 256;
+  int threads = n > 256 ? 1024 : (n >= 128 ? 512 : 256);
   pivoted_cholesky_kernel<<<batch, threads, dyn, st>>>(K, n, ld, stride_k, LT, ldl, stride_l,
                                                        rel_tol, rank_out, dims, use_smem);
   BASD_LAUNCH_CHECK();

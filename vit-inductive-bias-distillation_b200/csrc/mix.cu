@@ -30,19 +30,19 @@ __device__ __forceinline__ void taps(int i, int n_src, int n_dst, int& lo, int& 
 }
 
 template <typename T>
-__global__ void attn_rows_kernel(const T* __restrict__ attn, int H, int side, int has_cls,
-                                 int n_tok, float* __restrict__ rows) {
+__global__ void attn_rows_kernel(const T* __restrict__ attn, int H, int side, int q_rows,
+                                 int has_cls, int n_tok, float* __restrict__ rows) {
   const int b = blockIdx.x;
-  const T* base = attn + (long)b * H * side * side;
+  const T* base = attn + (long)b * H * q_rows * side;
   for (int n = threadIdx.x; n < n_tok; n += blockDim.x) {
     float s = 0.f;
-    if (has_cls) {
-      for (int h = 0; h < H; ++h) s += to_f32<T>(base[(long)h * side * side + 1 + n]);
+    if (has_cls) {    // CLS query row (row 0), keys 1..N
+      for (int h = 0; h < H; ++h) s += to_f32<T>(base[(long)h * q_rows * side + 1 + n]);
       s /= (float)H;
     } else {
       for (int h = 0; h < H; ++h)
-        for (int q = 0; q < side; ++q) s += to_f32<T>(base[((long)h * side + q) * side + n]);
-      s /= (float)(H * side);
+        for (int q = 0; q < q_rows; ++q) s += to_f32<T>(base[((long)h * q_rows + q) * side + n]);
+      s /= (float)(H * q_rows);
     }
     rows[(long)b * n_tok + n] = s;
   }
@@ -274,14 +274,15 @@ __global__ void weight_grad_finish_kernel(const float* __restrict__ partial, int
 using namespace basd;
 #define ST ((cudaStream_t)stream)
 
-extern "C" int basd_attn_rows(const void* attn, int dtype, int B, int H, int side, int has_cls,
-                              float* rows, void* stream) {
+extern "C" int basd_attn_rows(const void* attn, int dtype, int B, int H, int side, int q_rows,
+                              int has_cls, float* rows, void* stream) {
   const int n_tok = has_cls ? side - 1 : side;
   if (dtype == BASD_DTYPE_BF16)
-    attn_rows_kernel<__nv_bfloat16><<<B, 256, 0, ST>>>((const __nv_bfloat16*)attn, H, side, has_cls,
-                                                       n_tok, rows);
+    attn_rows_kernel<__nv_bfloat16><<<B, 256, 0, ST>>>((const __nv_bfloat16*)attn, H, side, q_rows,
+                                                       has_cls, n_tok, rows);
   else
-    attn_rows_kernel<float><<<B, 256, 0, ST>>>((const float*)attn, H, side, has_cls, n_tok, rows);
+    attn_rows_kernel<float><<<B, 256, 0, ST>>>((const float*)attn, H, side, q_rows, has_cls, n_tok,
+                                               rows);
   BASD_LAUNCH_CHECK();
   return 0;
 }
