@@ -40,36 +40,54 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks/throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons DURING the timed region through in-process NVML
+    (a polling `nvidia-smi` subprocess perturbs the launch thread); falls back to one
+    `nvidia-smi` query if NVML is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.mhz, self.mask, self.max_mhz, self.stop_flag = index, [], 0, None, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is None:
+            return
+        n = self.nvml
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                self.mhz.append(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    n.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.mask |= int(get(self.handle))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
-                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        if self.nvml is None or not self.mhz:
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=10).stdout.split(",")
+                return {"sm_mhz": int(out[0]), "sm_max_mhz": int(out[1]), "reasons": ["unsampled"]}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(self.mhz)
+        reasons = [k for k, bit in self.REASONS.items() if self.mask & bit]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(mhz)}
 
 
 def build_module(work, device, impl="b200"):

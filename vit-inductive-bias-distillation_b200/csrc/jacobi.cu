@@ -367,6 +367,156 @@ jacobi_rows_grouped_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
   if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
 }
 
+// Register-resident variant (odd-even transposition ordering).  Each group of LP lanes OWNS two
+// rows in registers (positions 2g and 2g+1 of a line).  Even steps rotate the resident pair and
+// touch no shared memory at all; odd steps rotate (2g+1, 2g+2): the left row of every group is
+// parked in a shared-memory exchange buffer, the left neighbour pairs it with its own right row
+// and hands the result back.  After every rotation the two rows trade places, so in n steps every
+// pair has met exactly once (the odd-even transposition network).  Shared-memory traffic per pair
+// is half that of the round-robin kernel, which ncu showed to be shared-memory-bandwidth bound.
+// All reloads are unconditional so at most two rows are ever live in registers.
+template <int LP, int NV>
+__device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, float4 (&y)[NV],
+                                                float& ny, bool valid, float tol2, float zero_thr,
+                                                float& worst) {
+  float ga = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    ga = fmaf(x[v].x, y[v].x, ga); ga = fmaf(x[v].y, y[v].y, ga);
+    ga = fmaf(x[v].z, y[v].z, ga); ga = fmaf(x[v].w, y[v].w, ga);
+  }
+#pragma unroll
+  for (int o = LP >> 1; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);
+  if (!valid) return;
+  const bool rot = (ga * ga > tol2 * nx * ny) && nx > zero_thr && ny > zero_thr;   // group-uniform
+  float c = 1.f, sn = 0.f, t = 0.f;
+  if (rot) {
+    worst = fmaxf(worst, __fdividef(ga * ga, nx * ny));
+    const float d = ny - nx;
+    const float h = fmaf(d, d, 4.f * ga * ga);
+    const float root = h * rsqrtf(h);
+    t = __fdividef(2.f * fabsf(ga), fabsf(d) + root);
+    t = ((d < 0.f) != (ga < 0.f)) ? -t : t;
+    const float w2 = fmaf(t, t, 1.f);
+    c = rsqrtf(w2);
+    c = c * fmaf(-0.5f * w2, c * c, 1.5f);
+    sn = c * t;
+  }
+  // x' = c x - s y, y' = s x + c y, then the rows trade places: x <- y', y <- x'
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 a = x[v], b = y[v];
+    x[v].x = fmaf(sn, a.x, c * b.x); y[v].x = fmaf(c, a.x, -sn * b.x);
+    x[v].y = fmaf(sn, a.y, c * b.y); y[v].y = fmaf(c, a.y, -sn * b.y);
+    x[v].z = fmaf(sn, a.z, c * b.z); y[v].z = fmaf(c, a.z, -sn * b.z);
+    x[v].w = fmaf(sn, a.w, c * b.w); y[v].w = fmaf(c, a.w, -sn * b.w);
+  }
+  const float nxp = fmaxf(fmaf(-t, ga, nx), 0.f), nyp = fmaxf(fmaf(t, ga, ny), 0.f);
+  nx = nyp;
+  ny = nxp;
+}
+
+template <int LP, int NV, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                           const int* __restrict__ dims, float tol, int max_sweeps,
+                           int* __restrict__ sweeps_out) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red_scratch[32];
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  const int gid = tid / LP, gl = tid % LP;
+  float* Gg = Gbase + (long)prob * stride;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
+  const int mv = (mm + 3) >> 2;
+  const int ldw = (((m + 3) >> 2) << 2);                 // exchange-buffer row pitch (>= 4*NV*LP? no: padded below)
+  float* xbuf = smem;                                    // (n/2 + 1) rows of LP*NV quads
+  const int pitch = LP * NV * 4;                         // every lane may touch all its NV quads
+  float* xn = smem + (size_t)((n + 1) / 2 + 1) * pitch;  // squared norms of the parked rows
+  (void)ldw;
+  const int h = (nn + 1) >> 1;                           // groups; the last one has no right row if nn is odd
+  const bool active = gid < h;
+  const int row_a = 2 * gid, row_b = 2 * gid + 1;
+  const bool has_b = active && row_b < nn;
+  float4 a[NV], b[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int idx = gl + LP * v;
+    a[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b[v] = a[v];
+    if (active && idx < mv) {
+      const int c4 = idx * 4;
+      a[v] = *reinterpret_cast<const float4*>(Gg + (long)row_a * ld + c4);
+      if (has_b) b[v] = *reinterpret_cast<const float4*>(Gg + (long)row_b * ld + c4);
+      if (c4 + 1 >= mm) { a[v].y = 0.f; b[v].y = 0.f; }
+      if (c4 + 2 >= mm) { a[v].z = 0.f; b[v].z = 0.f; }
+      if (c4 + 3 >= mm) { a[v].w = 0.f; b[v].w = 0.f; }
+    }
+  }
+  const float tol2 = tol * tol;
+  const int slot = min(gid, (n + 1) / 2);                // parking slot (inactive groups share the spare one)
+  float4* my_slot = reinterpret_cast<float4*>(xbuf + (size_t)slot * pitch);
+  float4* right_slot = reinterpret_cast<float4*>(xbuf + (size_t)min(gid + 1, (n + 1) / 2) * pitch);
+  int sweep = 0;
+  for (; sweep < max_sweeps && nn >= 2; ++sweep) {
+    float na = 0.f, nb = 0.f;                             // refresh the carried norms
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      na = fmaf(a[v].x, a[v].x, na); na = fmaf(a[v].y, a[v].y, na);
+      na = fmaf(a[v].z, a[v].z, na); na = fmaf(a[v].w, a[v].w, na);
+      nb = fmaf(b[v].x, b[v].x, nb); nb = fmaf(b[v].y, b[v].y, nb);
+      nb = fmaf(b[v].z, b[v].z, nb); nb = fmaf(b[v].w, b[v].w, nb);
+    }
+#pragma unroll
+    for (int o = LP >> 1; o > 0; o >>= 1) {
+      na += __shfl_xor_sync(0xffffffffu, na, o);
+      nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    }
+    const float mx = block_max(fmaxf(na, nb), red_scratch);
+    const float zero_thr = 1e-14f * mx;
+    float worst = 0.f;
+    for (int step = 0; step < nn; ++step) {
+      if ((step & 1) == 0) {
+        rotate_and_swap<LP, NV>(a, na, b, nb, has_b, tol2, zero_thr, worst);
+      } else {
+        // park the left row of every group; the left neighbour pairs it with its right row
+#pragma unroll
+        for (int v = 0; v < NV; ++v) my_slot[gl + LP * v] = a[v];
+        if (gl == 0) xn[slot] = na;
+        __syncthreads();
+        const bool pair_ok = has_b && (gid + 1 < h);
+        float4 y[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) y[v] = right_slot[gl + LP * v];
+        float ny = xn[min(gid + 1, (n + 1) / 2)];
+        rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst);
+        if (pair_ok) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) right_slot[gl + LP * v] = y[v];
+          if (gl == 0) xn[gid + 1] = ny;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < NV; ++v) a[v] = my_slot[gl + LP * v];
+        na = xn[slot];
+      }
+    }
+    worst = block_max(worst, red_scratch);
+    if (worst < tol) { ++sweep; break; }
+  }
+  if (active) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int idx = gl + LP * v;
+      if (idx < mv) {
+        *reinterpret_cast<float4*>(Gg + (long)row_a * ld + idx * 4) = a[v];
+        if (has_b) *reinterpret_cast<float4*>(Gg + (long)row_b * ld + idx * 4) = b[v];
+      }
+    }
+  }
+  if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
+}
+
 // Cluster variant for the few-but-large problems (projected-Gram eigenproblems, k x k
 // principal-angle SVDs: n up to 1024, a few dozen problems).  One thread-block CLUSTER per
 // problem: the matrix stays L2-resident in global memory, the n/2 independent row pairs of a
@@ -621,6 +771,22 @@ static int launch_cluster(float* G, int n, int m, int ld, long stride, int batch
 }
 
 template <int LP, int NV, int MAXT>
+static int launch_oddeven(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st) {
+  const size_t slots = (size_t)(n + 1) / 2 + 1;
+  const size_t dyn = (slots * LP * NV * 4 + slots + 4) * sizeof(float);
+  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oddeven_kernel<LP, NV, MAXT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int threads = ((n + 1) / 2) * LP;
+  threads = (threads + 31) / 32 * 32;
+  if (threads < 64) threads = 64;
+  jacobi_rows_oddeven_kernel<LP, NV, MAXT><<<batch, threads, dyn, st>>>(
+      G, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int LP, int NV, int MAXT>
 static int launch_grouped(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                           float tol, int max_sweeps, int* sweeps_out, size_t dyn, cudaStream_t st) {
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_grouped_kernel<LP, NV, MAXT>,
@@ -670,7 +836,21 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
   const int quads = (m + 3) / 4;
   // shared-memory resident path: LP lanes per pair
   const size_t need = ((size_t)n * quads * 4 + n) * sizeof(float);
-  const bool legacy = getenv("BASD_JACOBI_LEGACY") != nullptr;   // A/B debugging aid
+  const bool legacy = getenv("BASD_JACOBI_LEGACY") != nullptr;   // A/B debugging aids
+  const bool no_oddeven = getenv("BASD_JACOBI_ROUNDROBIN") != nullptr;
+  // register-resident odd-even kernel: every row pair needs its own group of 8 lanes
+  if (!legacy && !no_oddeven && ((n + 1) / 2) * 8 <= 800 && quads <= 56) {
+#define BASD_OE(NV, MAXT) \
+  return launch_oddeven<8, NV, MAXT>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st)
+    if (quads <= 8) BASD_OE(1, 800);
+    if (quads <= 16) BASD_OE(2, 800);
+    if (quads <= 24) BASD_OE(3, 800);
+    if (quads <= 32) BASD_OE(4, 800);
+    if (quads <= 40) BASD_OE(5, 800);
+    if (quads <= 48) BASD_OE(6, 800);
+    BASD_OE(7, 800);
+#undef BASD_OE
+  }
   if (!legacy && need + 1024 <= (size_t)smem_limit()) {
 #define BASD_GROUPED(LP, NV, MAXT) \
   return launch_grouped<LP, NV, MAXT>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, need, st)
