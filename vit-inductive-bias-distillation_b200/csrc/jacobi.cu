@@ -420,19 +420,23 @@ template <int LP, int NV, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                            const int* __restrict__ dims, float tol, int max_sweeps,
-                           int* __restrict__ sweeps_out) {
+                           int* __restrict__ sweeps_out, int dim_lo, int dim_hi) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_scratch[32];
   const int prob = blockIdx.x, tid = threadIdx.x;
+  // size window: lets the host launch this kernel and the cluster kernel back to back on the
+  // same batch, each taking the problems whose (device-resident) size suits it -- no host sync
+  if (dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;
   const int gid = tid / LP, gl = tid % LP;
   float* Gg = Gbase + (long)prob * stride;
   const int nn = dims ? min(dims[prob], n) : n;
   const int mm = dims ? min(dims[prob], m) : m;
   const int mv = (mm + 3) >> 2;
   const int ldw = (((m + 3) >> 2) << 2);                 // exchange-buffer row pitch (>= 4*NV*LP? no: padded below)
-  float* xbuf = smem;                                    // (n/2 + 1) rows of LP*NV quads
+  float* xbuf = smem;                                    // (cap/2 + 1) rows of LP*NV quads
   const int pitch = LP * NV * 4;                         // every lane may touch all its NV quads
-  float* xn = smem + (size_t)((n + 1) / 2 + 1) * pitch;  // squared norms of the parked rows
+  const int cap = dims ? min(n, dim_hi) : n;             // largest problem this launch accepts
+  float* xn = smem + (size_t)((cap + 1) / 2 + 1) * pitch;  // squared norms of the parked rows
   (void)ldw;
   const int h = (nn + 1) >> 1;                           // groups; the last one has no right row if nn is odd
   const bool active = gid < h;
@@ -454,9 +458,10 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
     }
   }
   const float tol2 = tol * tol;
-  const int slot = min(gid, (n + 1) / 2);                // parking slot (inactive groups share the spare one)
+  const int spare = (cap + 1) / 2;
+  const int slot = min(gid, spare);                      // parking slot (inactive groups share the spare one)
   float4* my_slot = reinterpret_cast<float4*>(xbuf + (size_t)slot * pitch);
-  float4* right_slot = reinterpret_cast<float4*>(xbuf + (size_t)min(gid + 1, (n + 1) / 2) * pitch);
+  float4* right_slot = reinterpret_cast<float4*>(xbuf + (size_t)min(gid + 1, spare) * pitch);
   int sweep = 0;
   for (; sweep < max_sweeps && nn >= 2; ++sweep) {
     float na = 0.f, nb = 0.f;                             // refresh the carried norms
@@ -488,7 +493,7 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
         float4 y[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) y[v] = right_slot[gl + LP * v];
-        float ny = xn[min(gid + 1, (n + 1) / 2)];
+        float ny = xn[min(gid + 1, spare)];
         rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst);
         if (pair_ok) {
 #pragma unroll
@@ -527,10 +532,11 @@ template <int NV, int R, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 jacobi_rows_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                            const int* __restrict__ dims, float tol, int max_sweeps,
-                           int* __restrict__ sweeps_out) {
+                           int* __restrict__ sweeps_out, int dim_lo, int dim_hi) {
   cg::cluster_group cluster = cg::this_cluster();
   const int csize = cluster.num_blocks(), crank = cluster.block_rank();
   const int prob = blockIdx.x / csize;
+  if (dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;   // whole cluster exits together
   __shared__ int flag;                                   // rank 0's copy is the cluster flag
   __shared__ float red_scratch[32];
   int* flag0 = cluster.map_shared_rank(&flag, 0);
@@ -748,7 +754,8 @@ static int sm_count() {
 
 template <int NV, int R, int MAXT>
 static int launch_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
-                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st) {
+                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st,
+                          int dim_lo = 0, int dim_hi = 1 << 30) {
   int csize = 8;
   while (csize > 1 && (long)batch * csize > sm_count()) csize >>= 1;
   const int half = (n + 1) / 2;
@@ -766,22 +773,24 @@ static int launch_cluster(float* G, int n, int m, int ld, long stride, int batch
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_cluster_kernel<NV, R, MAXT>, G, n, m, ld, stride,
-                               dims, tol, max_sweeps, sweeps_out));
+                               dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi));
   return 0;
 }
 
 template <int LP, int NV, int MAXT>
 static int launch_oddeven(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
-                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st) {
-  const size_t slots = (size_t)(n + 1) / 2 + 1;
+                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st,
+                          int dim_lo = 0, int dim_hi = 1 << 30) {
+  const int cap = (dims && dim_hi < n) ? dim_hi : n;
+  const size_t slots = (size_t)(cap + 1) / 2 + 1;
   const size_t dyn = (slots * LP * NV * 4 + slots + 4) * sizeof(float);
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oddeven_kernel<LP, NV, MAXT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  int threads = ((n + 1) / 2) * LP;
+  int threads = ((cap + 1) / 2) * LP;
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;
   jacobi_rows_oddeven_kernel<LP, NV, MAXT><<<batch, threads, dyn, st>>>(
-      G, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out);
+      G, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi);
   BASD_LAUNCH_CHECK();
   return 0;
 }
@@ -867,16 +876,26 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
 #undef BASD_GROUPED
   }
   const int nv = (quads + 31) / 32;
+  int lo = 0;
+  if (!legacy && !no_oddeven && dims && n == m) {
+    // square problems with a device-side active size (k x k principal-angle SVDs): those with
+    // k <= 200 run register/shared-memory resident, the rest on the cluster kernel below
+    constexpr int SMALL = 200;
+    if (int e = launch_oddeven<8, 7, 800>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
+                                          sweeps_out, st, 0, SMALL))
+      return e;
+    lo = SMALL + 1;
+  }
   if (!legacy) {
     switch (nv) {
-      case 1: return launch_cluster<1, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
-      case 2: return launch_cluster<2, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
-      case 3: return launch_cluster<3, 2, 768>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
-      case 4: return launch_cluster<4, 1, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+      case 1: return launch_cluster<1, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
+      case 2: return launch_cluster<2, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
+      case 3: return launch_cluster<3, 2, 768>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
+      case 4: return launch_cluster<4, 1, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
       case 5: case 6:
-        return launch_cluster<6, 1, 512>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+        return launch_cluster<6, 1, 512>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
       case 7: case 8:
-        return launch_cluster<8, 1, 512>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st);
+        return launch_cluster<8, 1, 512>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
       default: return -4;
     }
   }
