@@ -92,6 +92,13 @@ int basd_center_gram(const float* G, const float* colsum, int D, float inv_rows,
 int basd_mp_rank(const float* lam, int D, long rows, int cap, int* ranks, float* edges, int layers,
                  void* stream);
 
+/* Same rank from the eigendecomposition of the CENTRED second moment: the uncentred one is a
+ * rank-one update (+ rho c c^T, y = V^T c), whose eigenvalue counting function
+ * #{mu > x} = #{lam > x} + [1 + rho sum y_j^2/(lam_j - x) < 0] gives the lower median by bisection
+ * and the rank by one evaluation.  edges (optional): (layers, 3) = median, lambda_plus, tie flag. */
+int basd_mp_rank_secular(const float* lam_c, const float* y, int D, long rows, int cap, int* ranks,
+                         float* edges, int layers, void* stream);
+
 int basd_expand_ranks(const int* ranks, int E, int L, int* dims, void* stream);
 int basd_mask_block(const float* src, float* dst, int D, const int* dims, int batch, void* stream);
 

@@ -245,3 +245,30 @@ def test_procrustes_stage_value_and_gradients(n, d_s, d_t, rank_t):
     ref.backward()
     assert abs(float(pro.geo) - float(ref)) / abs(float(ref)) < 1e-3
     assert cosine(grads[0].cpu(), sg.grad) > 0.999
+
+
+def test_mp_rank_secular_matches_direct_spectrum():
+    """Rank from (centred eigendecomposition + secular equation) == rank from the uncentred spectrum."""
+    eng = _eng()
+    from basd_b200._native import call, ptr, stream
+    from oracle import kernel_model as km
+    torch.manual_seed(11)
+    d, rows, layers = 192, 2048, 6
+    x = torch.randn(layers, rows, d, device=DEV) * torch.logspace(0, -2, d, device=DEV) + \
+        torch.randn(layers, 1, d, device=DEV) * 0.7          # sizeable mean: centring matters
+    gram = x.transpose(1, 2) @ x
+    gram = 0.5 * (gram + gram.transpose(1, 2))
+    col = x.sum(1)
+    kc = gram - col.unsqueeze(2) * col.unsqueeze(1) / rows
+    lam, vt = eng.sym_eig(kc.contiguous())
+    y = torch.einsum("lij,lj->li", vt, col).contiguous()
+    ranks = torch.zeros(layers, dtype=torch.int32, device=DEV)
+    edges = torch.zeros(layers, 3, device=DEV)
+    call("basd_mp_rank_secular", ptr(lam), ptr(y), d, rows, d - 1, ptr(ranks), ptr(edges), layers, stream())
+    for i in range(layers):
+        spec = torch.linalg.eigvalsh(gram[i].double().cpu()).flip(0).float()
+        want = km.mp_rank_from_spectrum(spec, rows, d - 1)
+        n = spec.numel()
+        med = spec.flip(0)[(n - 1) // 2]
+        assert abs(float(edges[i, 0]) - float(med)) / float(med) < 1e-4
+        assert int(ranks[i]) == want or edges[i, 2] == 1

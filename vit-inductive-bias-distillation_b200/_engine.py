@@ -170,8 +170,7 @@ def attention_only_stats(teachers, attns, has_cls):
 @dataclass
 class SelectorState:
     ranks: torch.Tensor       # (L,) int32
-    edges: torch.Tensor       # (L,2) median, lambda_plus
-    lam_u: torch.Tensor       # (L, Ds) spectrum of the uncentred teacher second moment
+    edges: torch.Tensor       # (L,3) median, lambda_plus, tie flag (an eigenvalue within 1e-4 of the edge)
     lam_t: torch.Tensor       # (L, Ds) centred teacher eigenvalues
     lam_s: torch.Tensor       # (E, Ds)
     vt_s: torch.Tensor        # (E, Ds, Ds)
@@ -208,18 +207,21 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     chat_s = _f32(e, d_s, device=dev)
     sgemm(0, 1, e, d_s, d_s, stats.col_s, d_s, 0, proj_s, d_s, 0, chat_s, d_s, 0, 1)
 
-    # --- [uncentred teacher | centred teacher | centred student] eigenproblems in one batch
-    kall = _f32(2 * l + e, d_s, d_s, device=dev)
-    call("basd_center_gram", ptr(ghat_t), None, d_s, 0.0, ptr(kall[:l]), l, stream())
-    call("basd_center_gram", ptr(ghat_t), ptr(chat_t), d_s, 1.0 / rows_t, ptr(kall[l:2 * l]), l, stream())
-    call("basd_center_gram", ptr(ghat_s), ptr(chat_s), d_s, 1.0 / rows_s, ptr(kall[2 * l:]), e, stream())
+    # --- [centred teacher | centred student] eigenproblems in one batch.  The uncentred teacher
+    # spectrum (only needed for the MP rank) follows from the centred one by the rank-one
+    # secular equation, so it costs no eigenproblem of its own.
+    kall = _f32(l + e, d_s, d_s, device=dev)
+    call("basd_center_gram", ptr(ghat_t), ptr(chat_t), d_s, 1.0 / rows_t, ptr(kall[:l]), l, stream())
+    call("basd_center_gram", ptr(ghat_s), ptr(chat_s), d_s, 1.0 / rows_s, ptr(kall[l:]), e, stream())
     lam, vt = sym_eig(kall)
-    lam_u, lam_t, lam_s = lam[:l], lam[l:2 * l], lam[2 * l:]
-    vt_t, vt_s = vt[l:2 * l], vt[2 * l:]
-
+    lam_t, lam_s = lam[:l], lam[l:]
+    vt_t, vt_s = vt[:l], vt[l:]
+    y_t = _f32(l, d_s, device=dev)                        # y = V^T c_hat per teacher layer
+    sgemm(0, 0, d_s, 1, d_s, vt_t, d_s, d_s * d_s, chat_t, 1, d_s, y_t, 1, d_s, l)
     ranks = torch.empty(l, dtype=torch.int32, device=dev)
-    edges = _f32(l, 2, device=dev)
-    call("basd_mp_rank", ptr(lam_u), d_s, rows_t, d_s - 1, ptr(ranks), ptr(edges), l, stream())
+    edges = _f32(l, 3, device=dev)
+    call("basd_mp_rank_secular", ptr(lam_t), ptr(y_t), d_s, rows_t, d_s - 1, ptr(ranks), ptr(edges), l,
+         stream())
     dims = torch.empty(e * l, dtype=torch.int32, device=dev)
     call("basd_expand_ranks", ptr(ranks), e, l, ptr(dims), stream())
 
@@ -246,7 +248,7 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     temps = _f32(e, device=dev)
     call("basd_mix_weights", ptr(dist_el), ptr(log_temps), e, l, ptr(weights), ptr(temps), stream())
     mean_s = stats.col_s / float(rows_s)
-    return SelectorState(ranks, edges, lam_u, lam_t, lam_s, vt_s, wfull, uxt, vxt, sig, dist_el,
+    return SelectorState(ranks, edges, lam_t, lam_s, vt_s, wfull, uxt, vxt, sig, dist_el,
                          weights, temps, mean_s, {"kxk": sweeps})
 
 

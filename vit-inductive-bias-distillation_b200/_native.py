@@ -30,6 +30,7 @@ _SIG = {
     "basd_rowdot": [_p, _i, _l, _p, _i, _l, _i, _i, _i, _p, _p],
     "basd_center_gram": [_p, _p, _i, _f, _p, _i, _p],
     "basd_mp_rank": [_p, _i, _l, _i, _p, _p, _i, _p],
+    "basd_mp_rank_secular": [_p, _p, _i, _l, _i, _p, _p, _i, _p],
     "basd_expand_ranks": [_p, _i, _i, _p, _p],
     "basd_mask_block": [_p, _p, _i, _p, _i, _p],
     "basd_angle_distance": [_p, _p, _p, _i, _i, _i, _p, _p],

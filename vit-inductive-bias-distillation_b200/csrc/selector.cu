@@ -52,6 +52,83 @@ __global__ void mp_rank_kernel(const float* __restrict__ lam, int D, float aspec
   }
 }
 
+// MP rank of the UNCENTRED second moment from the eigendecomposition of the CENTRED one.
+// K_u = K_c + rho * c c^T is a rank-one update, so with K_c = V diag(lam) V^T and y = V^T c the
+// eigenvalues mu of K_u are the roots of the secular function
+//     f(x) = 1 + rho * sum_j y_j^2 / (lam_j - x),
+// they interlace the lam_j, and  #{mu > x} = #{lam > x} + [f(x) < 0].   That counting function
+// is monotone in x, so the lower median (torch.median, layer_selector.py:17) is found by
+// bisection on it and the rank (:19) is one more evaluation -- no second eigenproblem per
+// teacher layer.  fp64 for the (tiny) secular sums.  edges: (layers, 3) = median, lambda_plus,
+// tie flag (1 if the count changes within +-1e-4 relative of lambda_plus).
+__device__ int secular_count(const double* lam, const double* y2, int D, double rho, double x,
+                             double* red_d, int* red_i) {
+  double f = 0.0;
+  int c = 0;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    double diff = lam[j] - x;
+    c += diff > 0.0;
+    if (diff == 0.0) diff = 1e-300;
+    f += y2[j] / diff;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    f += __shfl_xor_sync(0xffffffffu, f, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) { red_d[warp] = f; red_i[warp] = c; }
+  __syncthreads();
+  f = 0.0;
+  c = 0;
+  for (int w = 0; w < nw; ++w) { f += red_d[w]; c += red_i[w]; }
+  return c + ((1.0 + rho * f) < 0.0 ? 1 : 0);
+}
+
+__global__ void mp_rank_secular_kernel(const float* __restrict__ lam_c, const float* __restrict__ y,
+                                       int D, double rho, float aspect, int cap,
+                                       int* __restrict__ ranks, float* __restrict__ edges) {
+  extern __shared__ double sd[];
+  double* lam = sd;          // D
+  double* y2 = sd + D;       // D
+  __shared__ double red_d[32];
+  __shared__ int red_i[32];
+  const int layer = blockIdx.x;
+  double hi = 0.0, ysum = 0.0;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const double l = (double)lam_c[(long)layer * D + j];
+    const double v = (double)y[(long)layer * D + j];
+    lam[j] = l;
+    y2[j] = v * v;
+  }
+  __syncthreads();
+  for (int j = 0; j < D; ++j) { hi = fmax(hi, lam[j]); ysum += y2[j]; }   // tiny, every thread
+  hi = hi + rho * ysum + 1e-30;                       // mu_max <= lam_max + rho |y|^2
+  double lo = fmin(0.0, -hi);                         // K_c is PSD up to rounding
+  const int want = D - (D - 1) / 2;                   // lower median = want-th largest
+  // largest x with #{mu > x} >= want  ==  the want-th largest root
+  for (int it = 0; it < 80; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    const int cnt = secular_count(lam, y2, D, rho, mid, red_d, red_i);
+    if (cnt >= want) lo = mid; else hi = mid;
+  }
+  const double median = 0.5 * (lo + hi);
+  const double root = 1.0 + sqrt((double)aspect);
+  const double edge = median * root * root;
+  const int rank = secular_count(lam, y2, D, rho, edge, red_d, red_i);
+  const int r_lo = secular_count(lam, y2, D, rho, edge * (1.0 - 1e-4), red_d, red_i);
+  const int r_hi = secular_count(lam, y2, D, rho, edge * (1.0 + 1e-4), red_d, red_i);
+  if (threadIdx.x == 0) {
+    ranks[layer] = min(rank, cap);
+    if (edges) {
+      edges[3 * layer] = (float)median;
+      edges[3 * layer + 1] = (float)edge;
+      edges[3 * layer + 2] = (r_lo != r_hi) ? 1.f : 0.f;
+    }
+  }
+}
+
 // dims[i*L + l] = ranks[l]
 __global__ void expand_ranks_kernel(const int* __restrict__ ranks, int E, int L,
                                     int* __restrict__ dims) {
@@ -216,6 +293,15 @@ extern "C" int basd_mp_rank(const float* lam, int D, long rows, int cap, int* ra
   if (layers <= 0) return 0;
   mp_rank_kernel<<<layers, 256, D * sizeof(float), ST>>>(lam, D, (float)((double)D / (double)rows),
                                                          cap, ranks, edges);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_mp_rank_secular(const float* lam_c, const float* y, int D, long rows, int cap,
+                                    int* ranks, float* edges, int layers, void* stream) {
+  if (layers <= 0) return 0;
+  mp_rank_secular_kernel<<<layers, 128, 2 * D * sizeof(double), ST>>>(
+      lam_c, y, D, 1.0 / (double)rows, (float)((double)D / (double)rows), cap, ranks, edges);
   BASD_LAUNCH_CHECK();
   return 0;
 }
