@@ -522,6 +522,142 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
   if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
 }
 
+// Cluster-wide register-resident odd-even Jacobi: the rows of ONE problem are spread over the
+// CTAs of a thread-block cluster (positions [crank*2*gpc, (crank+1)*2*gpc) live in CTA crank's
+// registers).  Even steps are purely register-local.  In odd steps every group parks its left row
+// in its CTA's shared memory; the only cross-CTA traffic is the single boundary row per CTA,
+// read and written back through distributed shared memory.  Two cluster barriers per odd step
+// replace the per-step cluster barrier + L2 round trips of jacobi_rows_cluster_kernel.
+__device__ __forceinline__ float cluster_max_nonneg(float v, cg::cluster_group& cluster, int* flag0,
+                                                    float* red) {
+  v = block_max(v, red);
+  if (threadIdx.x == 0) atomicMax(flag0, __float_as_int(v));
+  cluster.sync();
+  const float all = __int_as_float(*flag0);
+  return all;
+}
+
+template <int LP, int NV, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                              const int* __restrict__ dims, float tol, int max_sweeps,
+                              int* __restrict__ sweeps_out, int dim_lo, int dim_hi) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = cluster.num_blocks(), crank = cluster.block_rank();
+  const int prob = blockIdx.x / csize;
+  if (dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;     // whole cluster exits
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red_scratch[32];
+  __shared__ int cflag[2];
+  const int tid = threadIdx.x;
+  const int gpc = blockDim.x / LP;                        // groups (row pairs) per CTA
+  const int lgid = tid / LP, gl = tid % LP;
+  const int gid = crank * gpc + lgid;                     // global group index
+  float* Gg = Gbase + (long)prob * stride;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
+  const int mv = (mm + 3) >> 2;
+  constexpr int pitch = LP * NV * 4;
+  float* xbuf = smem;                                     // gpc + 1 parking slots
+  float* xn = smem + (size_t)(gpc + 1) * pitch;           // squared norms of the parked rows
+  const int h = (nn + 1) >> 1;
+  const bool active = gid < h;
+  const int row_a = 2 * gid, row_b = 2 * gid + 1;
+  const bool has_b = active && row_b < nn;
+  float4 a[NV], b[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int idx = gl + LP * v;
+    a[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b[v] = a[v];
+    if (active && idx < mv) {
+      const int c4 = idx * 4;
+      a[v] = *reinterpret_cast<const float4*>(Gg + (long)row_a * ld + c4);
+      if (has_b) b[v] = *reinterpret_cast<const float4*>(Gg + (long)row_b * ld + c4);
+      if (c4 + 1 >= mm) { a[v].y = 0.f; b[v].y = 0.f; }
+      if (c4 + 2 >= mm) { a[v].z = 0.f; b[v].z = 0.f; }
+      if (c4 + 3 >= mm) { a[v].w = 0.f; b[v].w = 0.f; }
+    }
+  }
+  const float tol2 = tol * tol;
+  float4* my_slot = reinterpret_cast<float4*>(xbuf + (size_t)lgid * pitch);
+  float* my_norm = xn + lgid;
+  // right neighbour's parking slot: next group of this CTA, or slot 0 of the next CTA (DSMEM)
+  float4* right_slot;
+  float* right_norm;
+  if (lgid + 1 < gpc) {
+    right_slot = reinterpret_cast<float4*>(xbuf + (size_t)(lgid + 1) * pitch);
+    right_norm = xn + lgid + 1;
+  } else if (crank + 1 < csize) {
+    right_slot = reinterpret_cast<float4*>(cluster.map_shared_rank(xbuf, crank + 1));
+    right_norm = cluster.map_shared_rank(xn, crank + 1);
+  } else {
+    right_slot = reinterpret_cast<float4*>(xbuf + (size_t)gpc * pitch);   // spare (never paired)
+    right_norm = xn + gpc;
+  }
+  int* flag0 = cluster.map_shared_rank(cflag, 0);
+  int sweep = 0;
+  for (; sweep < max_sweeps && nn >= 2; ++sweep) {
+    if (crank == 0 && tid == 0) { cflag[0] = 0; cflag[1] = 0; }
+    cluster.sync();
+    float na = 0.f, nb = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      na = fmaf(a[v].x, a[v].x, na); na = fmaf(a[v].y, a[v].y, na);
+      na = fmaf(a[v].z, a[v].z, na); na = fmaf(a[v].w, a[v].w, na);
+      nb = fmaf(b[v].x, b[v].x, nb); nb = fmaf(b[v].y, b[v].y, nb);
+      nb = fmaf(b[v].z, b[v].z, nb); nb = fmaf(b[v].w, b[v].w, nb);
+    }
+#pragma unroll
+    for (int o = LP >> 1; o > 0; o >>= 1) {
+      na += __shfl_xor_sync(0xffffffffu, na, o);
+      nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    }
+    const float mx = cluster_max_nonneg(fmaxf(na, nb), cluster, flag0, red_scratch);
+    const float zero_thr = 1e-14f * mx;
+    float worst = 0.f;
+    for (int step = 0; step < nn; ++step) {
+      if ((step & 1) == 0) {
+        rotate_and_swap<LP, NV>(a, na, b, nb, has_b, tol2, zero_thr, worst);
+      } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) my_slot[gl + LP * v] = a[v];
+        if (gl == 0) *my_norm = na;
+        cluster.sync();
+        const bool pair_ok = has_b && (gid + 1 < h);
+        float4 y[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) y[v] = right_slot[gl + LP * v];
+        float ny = *right_norm;
+        rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst);
+        if (pair_ok) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) right_slot[gl + LP * v] = y[v];
+          if (gl == 0) *right_norm = ny;
+        }
+        cluster.sync();
+#pragma unroll
+        for (int v = 0; v < NV; ++v) a[v] = my_slot[gl + LP * v];
+        na = *my_norm;
+      }
+    }
+    const float all_worst = cluster_max_nonneg(worst, cluster, flag0 + 1, red_scratch);
+    cluster.sync();                                       // all have read before rank 0 resets
+    if (all_worst < tol) { ++sweep; break; }
+  }
+  if (active) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int idx = gl + LP * v;
+      if (idx < mv) {
+        *reinterpret_cast<float4*>(Gg + (long)row_a * ld + idx * 4) = a[v];
+        if (has_b) *reinterpret_cast<float4*>(Gg + (long)row_b * ld + idx * 4) = b[v];
+      }
+    }
+  }
+  if (sweeps_out && crank == 0 && tid == 0) sweeps_out[prob] = sweep;
+}
+
 // Cluster variant for the few-but-large problems (projected-Gram eigenproblems, k x k
 // principal-angle SVDs: n up to 1024, a few dozen problems).  One thread-block CLUSTER per
 // problem: the matrix stays L2-resident in global memory, the n/2 independent row pairs of a
@@ -778,6 +914,34 @@ static int launch_cluster(float* G, int n, int m, int ld, long stride, int batch
 }
 
 template <int LP, int NV, int MAXT>
+static int launch_oe_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                             float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                             int dim_hi) {
+  const int gpc = MAXT / LP;                               // row pairs per CTA
+  int csize = 1;
+  while (csize < 8 && csize * gpc * 2 < n) csize <<= 1;
+  if (csize * gpc * 2 < n) return -12;                     // does not fit a portable cluster
+  const size_t dyn = ((size_t)(gpc + 1) * LP * NV * 4 + gpc + 2) * sizeof(float);
+  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe_cluster_kernel<LP, NV, MAXT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(batch * csize);
+  cfg.blockDim = dim3(gpc * LP);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_oe_cluster_kernel<LP, NV, MAXT>, G, n, m, ld, stride,
+                               dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi));
+  return 0;
+}
+
+template <int LP, int NV, int MAXT>
 static int launch_oddeven(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                           float tol, int max_sweeps, int* sweeps_out, cudaStream_t st,
                           int dim_lo = 0, int dim_hi = 1 << 30) {
@@ -885,6 +1049,18 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
                                           sweeps_out, st, 0, SMALL))
       return e;
     lo = SMALL + 1;
+  }
+  // register-resident rows spread over a cluster (16 lanes per pair, 48 pairs per CTA)
+  static const bool no_oe_cluster = getenv("BASD_JACOBI_L2CLUSTER") != nullptr;
+  if (!legacy && !no_oddeven && !no_oe_cluster && quads <= 16 * 7 && n <= 8 * 96) {
+    const int q16 = (quads + 15) / 16;
+#define BASD_OEC(NV) \
+  return launch_oe_cluster<16, NV, 768>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo, 1 << 30)
+    if (q16 <= 4) BASD_OEC(4);
+    if (q16 == 5) BASD_OEC(5);
+    if (q16 == 6) BASD_OEC(6);
+    BASD_OEC(7);
+#undef BASD_OEC
   }
   if (!legacy) {
     switch (nv) {
