@@ -28,7 +28,8 @@ __global__ void pivoted_cholesky_kernel(float* __restrict__ Kbase, int n, int ld
                                         float rel_tol, int* __restrict__ rank_out,
                                         const int* __restrict__ dims, int use_smem) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ unsigned long long best_key[2];   // (pivot value bits << 32) | ~index, double-buffered
+  __shared__ unsigned int best_val[2][32];     // per-warp best pivot (float bits), double-buffered
+  __shared__ int best_idx[2][32];
   const int prob = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
   float* Kg = Kbase + (long)prob * strideK;
@@ -46,32 +47,46 @@ __global__ void pivoted_cholesky_kernel(float* __restrict__ Kbase, int n, int ld
       for (int c = lane; c < lda; c += 32) As[r * lda + c] = (c < nn) ? Kg[(long)r * ld + c] : 0.f;
   }
   for (int i = tid; i < npad; i += T) colv[i] = 0.f;
-  if (tid < 2) best_key[tid] = 0ull;
+  if (tid < 64) { best_val[tid >> 5][tid & 31] = 0u; best_idx[tid >> 5][tid & 31] = 0; }
   __syncthreads();
-  auto pack = [](float v, int i) -> unsigned long long {
-    return (static_cast<unsigned long long>(__float_as_uint(fmaxf(v, 0.f))) << 32) |
-           static_cast<unsigned long long>(0xffffffffu - static_cast<unsigned>(i));
+  // warp-level argmax of non-negative floats: REDUX on the bit patterns, then the first lane
+  // that holds the maximum supplies the index
+  auto warp_argmax = [](float v, int i, unsigned& vbits, int& idx) {
+    const unsigned bits = __float_as_uint(fmaxf(v, 0.f));
+    vbits = __reduce_max_sync(0xffffffffu, bits);
+    const unsigned who = __ballot_sync(0xffffffffu, bits == vbits);
+    idx = __shfl_sync(0xffffffffu, i, __ffs(who) - 1);
   };
   float dmax = 0.f;
   {
-    unsigned long long mine = 0ull;
+    float bv = -1.f;
+    int bi = 0;
     for (int i = tid; i < nn; i += T) {
       const float d = A[(long)i * lda + i];
       diag[i] = d;
       dmax = fmaxf(dmax, d);
-      const unsigned long long k = pack(d, i);
-      mine = k > mine ? k : mine;
+      if (d > bv) { bv = d; bi = i; }
     }
-    if (mine) atomicMax(&best_key[0], mine);
+    unsigned vb;
+    int ib;
+    warp_argmax(bv, bi, vb, ib);
+    if (lane == 0) { best_val[0][warp] = vb; best_idx[0][warp] = ib; }
   }
   dmax = block_max(dmax, red);
   const float floor_v = rel_tol * dmax;
   __syncthreads();
   int rank = 0;
   for (int j = 0; j < nn; ++j) {
-    const unsigned long long key = best_key[j & 1];
-    const float best = __uint_as_float(static_cast<unsigned>(key >> 32));
-    const int p = static_cast<int>(0xffffffffu - static_cast<unsigned>(key & 0xffffffffu));
+    unsigned vb;
+    int p;
+    {   // every warp reduces the per-warp candidates redundantly: no extra barrier, no atomics
+      const unsigned cv = lane < nwarp ? best_val[j & 1][lane] : 0u;
+      const int ci = lane < nwarp ? best_idx[j & 1][lane] : 0;
+      vb = __reduce_max_sync(0xffffffffu, cv);
+      const unsigned who = __ballot_sync(0xffffffffu, cv == vb);
+      p = __shfl_sync(0xffffffffu, ci, __ffs(who) - 1);
+    }
+    const float best = __uint_as_float(vb);
     if (!(best > floor_v) || !(best > 0.f)) break;           // uniform across the block
     const float rs = rsqrtf(best);
     for (int i = tid; i < nn; i += T) {                      // column j of L = row p of the Schur complement
@@ -80,11 +95,11 @@ __global__ void pivoted_cholesky_kernel(float* __restrict__ Kbase, int n, int ld
       colv[i] = c;
       LT[(long)j * ldl + i] = c;
     }
-    if (tid == 0) best_key[(j + 1) & 1] = 0ull;
     __syncthreads();
     {   // rank-1 update (one warp per row, 128-bit chunks) fused with the next pivot search
       const int quads = lda >> 2;
-      unsigned long long mine = 0ull;
+      float bv = -1.f;
+      int bi = 0;
       for (int i = warp; i < nn; i += nwarp) {
         const float di = diag[i];
         if (di < 0.f) continue;                              // already eliminated
@@ -102,16 +117,129 @@ __global__ void pivoted_cholesky_kernel(float* __restrict__ Kbase, int n, int ld
         }
         const float nd = fmaxf(fmaf(-ci, ci, di), 0.f);
         if (lane == 0) diag[i] = nd;
-        const unsigned long long k = pack(nd, i);
-        mine = k > mine ? k : mine;
+        if (nd > bv) { bv = nd; bi = i; }                    // warp-uniform
       }
-      if (lane == 0 && mine) atomicMax(&best_key[(j + 1) & 1], mine);
+      if (lane == 0) {
+        best_val[(j + 1) & 1][warp] = __float_as_uint(fmaxf(bv, 0.f));
+        best_idx[(j + 1) & 1][warp] = bi;
+      }
     }
     __syncthreads();
     rank = j + 1;
   }
   __syncthreads();
   // zero the rest: rows >= rank, and (for dims) columns >= nn of every row
+  for (int e = tid; e < n * n; e += T) {
+    const int r = e / n, c = e - r * n;
+    if (r >= rank || c >= nn) LT[(long)r * ldl + c] = 0.f;
+  }
+  if (rank_out && tid == 0) rank_out[prob] = rank;
+}
+
+// Left-looking variant for matrices whose factor fits shared memory (n <= 224): step j forms only
+// the new column  col = (K[:,p] - sum_{k<j} L[:,k] L[p,k]) / sqrt(pivot)  from the factor rows
+// already in shared memory.  The Schur complement is never materialised (K stays untouched in
+// global memory; its pivot row is fetched from L2 while the dot products run), so a step reads
+// j*n floats and writes n, instead of reading and writing the whole n x n trailing matrix.
+template <int PARTS>
+__global__ void __launch_bounds__(1024, 1)
+pivoted_cholesky_left_kernel(const float* __restrict__ Kbase, int n, int ld, long strideK,
+                             float* __restrict__ LTbase, int ldl, long strideL, float rel_tol,
+                             int* __restrict__ rank_out, const int* __restrict__ dims) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ unsigned int best_val[2][32];
+  __shared__ int best_idx[2][32];
+  __shared__ float red[32];
+  const int prob = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+  const float* Kg = Kbase + (long)prob * strideK;
+  float* LT = LTbase + (long)prob * strideL;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int npad = (n + 31) & ~31;
+  float* Ls = smem;                       // npad x npad factor rows (row j = column j of L)
+  float* diag = Ls + (size_t)npad * npad; // npad
+  float* pacc = diag + npad;              // PARTS x npad partial dot products
+  const int wpp = npad >> 5;              // warps per part
+  const int part = warp / wpp;            // which slice of k this thread sums
+  const int i = (warp % wpp) * 32 + lane; // which row of the column it produces
+  const bool worker = part < PARTS;
+  auto warp_argmax = [](float v, int idx_in, unsigned& vbits, int& idx) {
+    const unsigned bits = __float_as_uint(fmaxf(v, 0.f));
+    vbits = __reduce_max_sync(0xffffffffu, bits);
+    const unsigned who = __ballot_sync(0xffffffffu, bits == vbits);
+    idx = __shfl_sync(0xffffffffu, idx_in, __ffs(who) - 1);
+  };
+  if (tid < 64) { best_val[tid >> 5][tid & 31] = 0u; best_idx[tid >> 5][tid & 31] = 0; }
+  __syncthreads();
+  float dmax = 0.f;
+  {
+    float bv = -1.f;
+    int bi = 0;
+    for (int r = tid; r < npad; r += T) {
+      const float d = r < nn ? Kg[(long)r * ld + r] : -1.f;
+      diag[r] = d;
+      dmax = fmaxf(dmax, d);
+      if (d > bv) { bv = d; bi = r; }
+    }
+    unsigned vb;
+    int ib;
+    warp_argmax(bv, bi, vb, ib);
+    if (lane == 0) { best_val[0][warp] = vb; best_idx[0][warp] = ib; }
+  }
+  dmax = block_max(dmax, red);
+  const float floor_v = rel_tol * dmax;
+  __syncthreads();
+  int rank = 0;
+  for (int j = 0; j < nn; ++j) {
+    unsigned vb;
+    int p;
+    {
+      const unsigned cv = lane < nwarp ? best_val[j & 1][lane] : 0u;
+      const int ci = lane < nwarp ? best_idx[j & 1][lane] : 0;
+      vb = __reduce_max_sync(0xffffffffu, cv);
+      const unsigned who = __ballot_sync(0xffffffffu, cv == vb);
+      p = __shfl_sync(0xffffffffu, ci, __ffs(who) - 1);
+    }
+    const float best = __uint_as_float(vb);
+    if (!(best > floor_v) || !(best > 0.f)) break;           // uniform across the block
+    // pivot row of K (== pivot column by symmetry): in flight while the dot products run
+    float kp = 0.f;
+    if (worker && part == 0 && i < nn) kp = __ldg(Kg + (long)p * ld + i);
+    if (worker) {
+      float acc = 0.f;
+      for (int k = part; k < j; k += PARTS)
+        acc = fmaf(Ls[(size_t)k * npad + i], Ls[(size_t)k * npad + p], acc);
+      pacc[part * npad + i] = acc;
+    }
+    __syncthreads();
+    float bv = -1.f;
+    int bi = 0;
+    if (worker && part == 0) {
+      float c = 0.f;
+      const float di = diag[i];
+      if (i < nn && di >= 0.f) {
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < PARTS; ++q) acc += pacc[q * npad + i];
+        c = (i == p) ? best * rsqrtf(best) : (kp - acc) * rsqrtf(best);
+        const float nd = (i == p) ? -1.f : fmaxf(fmaf(-c, c, di), 0.f);
+        diag[i] = nd;
+        bv = nd;
+        bi = i;
+      }
+      Ls[(size_t)j * npad + i] = c;
+      if (i < nn) LT[(long)j * ldl + i] = c;
+    }
+    {
+      unsigned vbn;
+      int ibn;
+      warp_argmax(bv, bi, vbn, ibn);
+      if (lane == 0) { best_val[(j + 1) & 1][warp] = vbn; best_idx[(j + 1) & 1][warp] = ibn; }
+    }
+    __syncthreads();
+    rank = j + 1;
+  }
+  __syncthreads();
   for (int e = tid; e < n * n; e += T) {
     const int r = e / n, c = e - r * n;
     if (r >= rank || c >= nn) LT[(long)r * ldl + c] = 0.f;
@@ -982,6 +1110,20 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
   using namespace basd;
   if (batch <= 0 || n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  {   // left-looking kernel: factor rows resident in shared memory
+    constexpr int PARTS = 4;
+    const size_t np32 = ((size_t)n + 31) & ~(size_t)31;
+    const size_t dyn_left = (np32 * np32 + np32 * (1 + PARTS)) * sizeof(float);
+    const int threads_left = (int)(np32 * PARTS);
+    if (!getenv("BASD_CHOL_RIGHT") && dyn_left + 2048 <= (size_t)smem_limit() && threads_left <= 1024) {
+      BASD_CUDA(cudaFuncSetAttribute(pivoted_cholesky_left_kernel<PARTS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_left));
+      pivoted_cholesky_left_kernel<PARTS><<<batch, threads_left, dyn_left, st>>>(
+          K, n, ld, stride_k, LT, ldl, stride_l, rel_tol, rank_out, dims);
+      BASD_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const size_t npad = ((size_t)n + 3) & ~(size_t)3;
   const size_t base = (size_t)(2 * npad + 32) * sizeof(float);
   const size_t staged = base + npad * npad * sizeof(float);
