@@ -129,11 +129,14 @@ def roofline(work, mod, args5, pk, clocks):
     """Per-entry-point CUDA-event timing of one extra (untimed) step; returns the roofline
     record of the dominant kernel plus a per-kernel table."""
     from basd_b200 import _native as nat
+    from basd_b200 import _engine as eng
     one_step(mod, *args5)
     torch.cuda.synchronize()
+    eng.jacobi_log = []
     nat.start_timeline()
     one_step(mod, *args5)
     tl = nat.stop_timeline()
+    jlog, eng.jacobi_log = eng.jacobi_log, None
     if os.environ.get("BASD_TIMELINE"):
         with open(os.environ["BASD_TIMELINE"], "w") as fh:
             for name, ms in tl:
@@ -148,6 +151,20 @@ def roofline(work, mod, args5, pk, clocks):
     fm = flop_model(work, None)
     sm_mhz = clocks.get("sm_mhz") or pk["sm_max_mhz"]
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    # Jacobi: algorithmic flops of the launches of this step = pair visits x one dot product (2m)
+    # + rotations actually applied x two rotated rows (6m); sweeps/rotation counts come from the device
+    jac_ms = [ms for name, ms in tl if name.startswith("basd_jacobi_rows")]
+    jac = []
+    for (tag, n, m, dims, sweeps, rot), ms in zip(jlog, jac_ms):
+        sw = sweeps.double().cpu()
+        kk = dims.double().cpu() if dims is not None else torch.full_like(sw, float(n))
+        visits = float((sw * kk * (kk - 1) / 2).sum())
+        flops = float((sw * kk * (kk - 1) / 2 * 2 * kk).sum() + (rot.double().cpu() * 6 * kk).sum())
+        jac.append({"kernel": f"basd_jacobi_rows[{tag}]", "ms": round(ms, 4), "problems": int(sw.numel()),
+                    "n": int(kk.max()), "sweeps_mean": round(float(sw.mean()), 2), "pair_visits": visits,
+                    "rotations": float(rot.sum()), "bound": "fp32", "achieved": flops / (ms * 1e-3) / 1e12,
+                    "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak,
+                    "share": round(ms / total, 4)})
     records = []
     for name, ms, cnt in table:
         rec = {"kernel": name, "ms": round(ms, 4), "launches": cnt, "share": round(ms / total, 4)}
@@ -159,6 +176,7 @@ def roofline(work, mod, args5, pk, clocks):
         if "achieved" in rec:
             rec["frac"] = rec["achieved"] / rec["peak"]
         records.append(rec)
+    records = sorted(records + jac, key=lambda r: -r["ms"])
     return records, total, fp32_peak
 
 
@@ -193,12 +211,16 @@ def run_b200(args):
     sampler.mask = 0
     launches0 = nat.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         loss = one_step(mod, *args5)
+        marks[i + 1].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     launches = nat.launch_count - launches0
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -292,6 +314,7 @@ def run_b200(args):
                    "token_dtype": str(work.token_dtype).replace("torch.", ""),
                    "cache": "inputs (>=1 GB tokens + attention maps per step) exceed the 126 MB L2",
                    "parallelism": f"dp{world}"},
+        "step_ms": [round(x, 2) for x in per_step],
         "clocks": clocks, "gpu_launches": launches // max(1, args.steps),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 4, "ms_per_step": round(float(t.item()), 3)},
@@ -299,9 +322,9 @@ def run_b200(args):
     # every rank runs the profiled step (the loss all-reduces inside); only rank 0 reports
     records, total, fp32_peak = roofline(work, mod, args5, pk, clocks)
     if rank == 0:
-        line["kernels"] = records[:12]
+        line["kernels"] = records[:14]
         line["kernel_ms_total"] = round(total, 3)
-        top = next((r for r in records if "achieved" in r), None)
+        top = next((r for r in records if "achieved" in r and "[" in r["kernel"] or "achieved" in r), None)
         if top:
             line["roofline"] = {"kernel": top["kernel"], "bound": top["bound"], "achieved": round(top["achieved"], 2),
                                 "peak": round(top["peak"], 2), "unit": top["unit"], "frac": round(top["frac"], 4),

@@ -71,6 +71,11 @@ int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, float* LT, int
 int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                      float tol, int max_sweeps, int* sweeps_out, void* stream);
 
+/* Same, and rot_out[problem] += number of plane rotations applied (for the roofline accounting). */
+int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,
+                             const int* dims, float tol, int max_sweeps, int* sweeps_out,
+                             int* rot_out, void* stream);
+
 /* Row norms -> vals (norm or norm^2), unit rows -> V, optional descending sort. */
 int basd_rows_normalize(const float* G, int n, int m, int ld, long stride, float* V, int ldv,
                         long stride_v, float* vals, int batch, int sort, int square,

@@ -63,8 +63,20 @@ def pivoted_cholesky(k, lt, rel_tol, dims=None, rank_out=None):
          ptr(rank_out), ptr(dims), stream())
 
 
-def jacobi_rows(g, dims=None, sweeps_out=None):
+# (name, n, m, sweeps, rotations) of every Jacobi launch of the last step, filled only while
+# `jacobi_log` is a list (bench.py's roofline leg turns it on for one step)
+jacobi_log = None
+
+
+def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi"):
     batch, n, m = g.shape
+    if jacobi_log is not None:
+        sweeps_out = sweeps_out if sweeps_out is not None else torch.zeros(batch, dtype=torch.int32, device=g.device)
+        rot = torch.zeros(batch, dtype=torch.int32, device=g.device)
+        call("basd_jacobi_rows_counted", ptr(g), n, m, m, n * m, batch, ptr(dims), JACOBI_TOL,
+             JACOBI_SWEEPS, ptr(sweeps_out), ptr(rot), stream())
+        jacobi_log.append((tag, n, m, dims, sweeps_out, rot))
+        return
     call("basd_jacobi_rows", ptr(g), n, m, m, n * m, batch, ptr(dims), JACOBI_TOL, JACOBI_SWEEPS,
          ptr(sweeps_out), stream())
 
@@ -84,7 +96,7 @@ def sym_eig(kmats: torch.Tensor):
     work = kmats.clone()
     lt = _f32(batch, d, d, device=dev)
     pivoted_cholesky(work, lt, GRAM_CHOL_TOL)
-    jacobi_rows(lt)
+    jacobi_rows(lt, tag="eig")
     vt = work                         # reuse: the Schur complement is dead
     coarse = _f32(batch, d, device=dev)
     rows_normalize(lt, vt, coarse, sort=True, square=True, rel_floor=ROW_FLOOR)
@@ -234,7 +246,7 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
         sgemm(0, 1, d_s, d_s, d_s, vt_t, d_s, dd, vt_s[i], d_s, 0, gx[i * l:], d_s, dd, l)
     call("basd_mask_block", ptr(gx), ptr(gx), d_s, ptr(dims), e * l, stream())
     sweeps = torch.zeros(e * l, dtype=torch.int32, device=dev)
-    jacobi_rows(gx, dims=dims, sweeps_out=sweeps)
+    jacobi_rows(gx, dims=dims, sweeps_out=sweeps, tag="kxk")
     uxt = _f32(e * l, d_s, d_s, device=dev)
     sig = _f32(e * l, d_s, device=dev)
     rows_normalize(gx, uxt, sig, sort=True, square=False, rel_floor=SV_FLOOR, dims=dims)
@@ -308,7 +320,7 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
     sgemm(0, 1, n, n, n, ls_t, n, nn, lt_t, n, nn, x0, n, nn, p)      # X   = L_s^T L_t
     sgemm(0, 1, n, n, n, lt_t, n, nn, ls_t, n, nn, g, n, nn, p)       # X^T
     sweeps = torch.zeros(p, dtype=torch.int32, device=dev)
-    jacobi_rows(g, sweeps_out=sweeps)                    # rows -> sigma_j u_j^T
+    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes")  # rows -> sigma_j u_j^T
     rows_normalize(g, g, None, sort=False, square=False, rel_floor=ROW_FLOOR)
     ut = g
     rows2 = _f32(p, n, n, device=dev)

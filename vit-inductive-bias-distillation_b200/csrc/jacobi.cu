@@ -506,7 +506,7 @@ jacobi_rows_grouped_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
 template <int LP, int NV>
 __device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, float4 (&y)[NV],
                                                 float& ny, bool valid, float tol2, float zero_thr,
-                                                float& worst) {
+                                                float& worst, int& nrot) {
   float ga = 0.f;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -519,6 +519,7 @@ __device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, floa
   const bool rot = (ga * ga > tol2 * nx * ny) && nx > zero_thr && ny > zero_thr;   // group-uniform
   float c = 1.f, sn = 0.f, t = 0.f;
   if (rot) {
+    ++nrot;
     worst = fmaxf(worst, __fdividef(ga * ga, nx * ny));
     const float d = ny - nx;
     const float h = fmaf(d, d, 4.f * ga * ga);
@@ -548,9 +549,11 @@ template <int LP, int NV, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                            const int* __restrict__ dims, float tol, int max_sweeps,
-                           int* __restrict__ sweeps_out, int dim_lo, int dim_hi) {
+                           int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
+                           int* __restrict__ rot_out) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_scratch[32];
+  int nrot = 0;
   const int prob = blockIdx.x, tid = threadIdx.x;
   // size window: lets the host launch this kernel and the cluster kernel back to back on the
   // same batch, each taking the problems whose (device-resident) size suits it -- no host sync
@@ -610,7 +613,7 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
     float worst = 0.f;
     for (int step = 0; step < nn; ++step) {
       if ((step & 1) == 0) {
-        rotate_and_swap<LP, NV>(a, na, b, nb, has_b, tol2, zero_thr, worst);
+        rotate_and_swap<LP, NV>(a, na, b, nb, has_b, tol2, zero_thr, worst, nrot);
       } else {
         // park the left row of every group; the left neighbour pairs it with its right row
 #pragma unroll
@@ -622,7 +625,7 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
 #pragma unroll
         for (int v = 0; v < NV; ++v) y[v] = right_slot[gl + LP * v];
         float ny = xn[min(gid + 1, spare)];
-        rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst);
+        rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst, nrot);
         if (pair_ok) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) right_slot[gl + LP * v] = y[v];
@@ -648,6 +651,10 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
     }
   }
   if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
+  if (rot_out) {                                         // rotations applied (one count per group)
+    const float tot = block_sum(gl == 0 ? (float)nrot : 0.f, red_scratch);
+    if (tid == 0) atomicAdd(rot_out + prob, (int)tot);
+  }
 }
 
 // Cluster-wide register-resident odd-even Jacobi: the rows of ONE problem are spread over the
@@ -669,7 +676,9 @@ template <int LP, int NV, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                               const int* __restrict__ dims, float tol, int max_sweeps,
-                              int* __restrict__ sweeps_out, int dim_lo, int dim_hi) {
+                              int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
+                              int* __restrict__ rot_out) {
+  int nrot = 0;
   cg::cluster_group cluster = cg::this_cluster();
   const int csize = cluster.num_blocks(), crank = cluster.block_rank();
   const int prob = blockIdx.x / csize;
@@ -746,7 +755,7 @@ jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, l
     float worst = 0.f;
     for (int step = 0; step < nn; ++step) {
       if ((step & 1) == 0) {
-        rotate_and_swap<LP, NV>(a, na, b, nb, has_b, tol2, zero_thr, worst);
+        rotate_and_swap<LP, NV>(a, na, b, nb, has_b, tol2, zero_thr, worst, nrot);
       } else {
 #pragma unroll
         for (int v = 0; v < NV; ++v) my_slot[gl + LP * v] = a[v];
@@ -757,7 +766,7 @@ jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, l
 #pragma unroll
         for (int v = 0; v < NV; ++v) y[v] = right_slot[gl + LP * v];
         float ny = *right_norm;
-        rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst);
+        rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst, nrot);
         if (pair_ok) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) right_slot[gl + LP * v] = y[v];
@@ -784,6 +793,10 @@ jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, l
     }
   }
   if (sweeps_out && crank == 0 && tid == 0) sweeps_out[prob] = sweep;
+  if (rot_out) {
+    const float tot = block_sum(gl == 0 ? (float)nrot : 0.f, red_scratch);
+    if (tid == 0) atomicAdd(rot_out + prob, (int)tot);
+  }
 }
 
 // Cluster variant for the few-but-large problems (projected-Gram eigenproblems, k x k
@@ -1044,7 +1057,7 @@ static int launch_cluster(float* G, int n, int m, int ld, long stride, int batch
 template <int LP, int NV, int MAXT>
 static int launch_oe_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                              float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
-                             int dim_hi) {
+                             int dim_hi, int* rot_out) {
   const int gpc = MAXT / LP;                               // row pairs per CTA
   int csize = 1;
   while (csize < 8 && csize * gpc * 2 < n) csize <<= 1;
@@ -1065,14 +1078,14 @@ static int launch_oe_cluster(float* G, int n, int m, int ld, long stride, int ba
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_oe_cluster_kernel<LP, NV, MAXT>, G, n, m, ld, stride,
-                               dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi));
+                               dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi, rot_out));
   return 0;
 }
 
 template <int LP, int NV, int MAXT>
 static int launch_oddeven(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                           float tol, int max_sweeps, int* sweeps_out, cudaStream_t st,
-                          int dim_lo = 0, int dim_hi = 1 << 30) {
+                          int dim_lo = 0, int dim_hi = 1 << 30, int* rot_out = nullptr) {
   const int cap = (dims && dim_hi < n) ? dim_hi : n;
   const size_t slots = (size_t)(cap + 1) / 2 + 1;
   const size_t dyn = (slots * LP * NV * 4 + slots + 4) * sizeof(float);
@@ -1082,7 +1095,7 @@ static int launch_oddeven(float* G, int n, int m, int ld, long stride, int batch
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;
   jacobi_rows_oddeven_kernel<LP, NV, MAXT><<<batch, threads, dyn, st>>>(
-      G, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi);
+      G, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi, rot_out);
   BASD_LAUNCH_CHECK();
   return 0;
 }
@@ -1141,9 +1154,22 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
 
 // Orthogonalises the rows of each (n x m) row-major matrix in place. ld % 4 == 0 and
 // 16-byte aligned bases are required (128-bit row accesses).
+extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,
+                                        const int* dims, float tol, int max_sweeps, int* sweeps_out,
+                                        int* rot_out, void* stream);
+
 extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int batch,
                                 const int* dims, float tol, int max_sweeps, int* sweeps_out,
                                 void* stream) {
+  return basd_jacobi_rows_counted(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out,
+                                  nullptr, stream);
+}
+
+// Same, additionally accumulating into rot_out[problem] the number of plane rotations applied
+// (bench.py's roofline leg; only the register-resident kernels count, others leave it untouched).
+extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,
+                                        const int* dims, float tol, int max_sweeps, int* sweeps_out,
+                                        int* rot_out, void* stream) {
   using namespace basd;
   if (batch <= 0 || n <= 0) return 0;
   if ((ld & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(G) & 15)) return -3;
@@ -1156,7 +1182,7 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
   // register-resident odd-even kernel: every row pair needs its own group of 8 lanes
   if (!legacy && !no_oddeven && ((n + 1) / 2) * 8 <= 800 && quads <= 56) {
 #define BASD_OE(NV, MAXT) \
-  return launch_oddeven<8, NV, MAXT>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st)
+  return launch_oddeven<8, NV, MAXT>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, 0, 1 << 30, rot_out)
     if (quads <= 8) BASD_OE(1, 800);
     if (quads <= 16) BASD_OE(2, 800);
     if (quads <= 24) BASD_OE(3, 800);
@@ -1188,7 +1214,7 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
     // k <= 200 run register/shared-memory resident, the rest on the cluster kernel below
     constexpr int SMALL = 200;
     if (int e = launch_oddeven<8, 7, 800>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
-                                          sweeps_out, st, 0, SMALL))
+                                          sweeps_out, st, 0, SMALL, rot_out))
       return e;
     lo = SMALL + 1;
   }
@@ -1197,7 +1223,7 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
   if (!legacy && !no_oddeven && !no_oe_cluster && quads <= 16 * 7 && n <= 8 * 96) {
     const int q16 = (quads + 15) / 16;
 #define BASD_OEC(NV) \
-  return launch_oe_cluster<16, NV, 768>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo, 1 << 30)
+  return launch_oe_cluster<16, NV, 768>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo, 1 << 30, rot_out)
     if (q16 <= 4) BASD_OEC(4);
     if (q16 == 5) BASD_OEC(5);
     if (q16 == 6) BASD_OEC(6);
