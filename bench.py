@@ -204,9 +204,10 @@ def run_b200(args):
 
     sampler = ClockSampler(local)          # NVML init and thread start-up stay outside the timed region
     sampler.start()
+    loss = None
     for _ in range(args.warmup):
-        one_step(mod, *args5)
-    barrier()
+        loss = one_step(mod, *args5)       # keep `loss` alive exactly like the timed loop does, so
+    barrier()                              # the caching allocator reaches its steady state here
     sampler.mhz.clear()
     sampler.mask = 0
     launches0 = nat.launch_count

@@ -9,6 +9,7 @@
 //   basd_token_gram    : G = X^T X (token space, symmetric, split-K, deterministic) and
 //                        c = X^T 1  (reference: layer_selector.py:13,35 after R4)
 #include "common.cuh"
+#include <cstdlib>
 
 namespace basd {
 
@@ -130,6 +131,147 @@ sgemm_kernel(int M, int N, int K, const AT* __restrict__ A, int lda, long sA,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float* dst = C + (long)m * ldc + n;
+      const float prev = (beta != 0.f) ? beta * (*dst) : 0.f;
+      *dst = scale * acc[i][j] + prev;
+    }
+  }
+}
+
+// Large-tile variant: 8x8 register micro-tiles (as four 4x4 quadrants so that every shared-memory
+// read is a conflict-free 128-bit load), BK = 8, double-buffered shared memory with the next
+// k-slab prefetched into registers while the current one is multiplied.  Tile widths 104 or 128:
+// two 104-wide tiles cover the 196-row per-sample matrices with 6 % waste.
+constexpr int BK8 = 8;
+
+template <bool TA, bool TB, typename AT, int TM, int TN>
+__global__ void __launch_bounds__((TM / 8) * (TN / 8))
+sgemm8_kernel(int M, int N, int K, const AT* __restrict__ A, int lda, long sA,
+              const float* __restrict__ a_shift, const float* __restrict__ B, int ldb, long sB,
+              float* __restrict__ C, int ldc, long sC, float alpha,
+              const float* __restrict__ alpha_dev, float beta, bool vec) {
+  constexpr int NT = (TM / 8) * (TN / 8), TXN = TN / 8;
+  constexpr int QA = TM * BK8 / 4, QB = TN * BK8 / 4;          // quads per slab
+  constexpr int RA = (QA + NT - 1) / NT, RB = (QB + NT - 1) / NT;
+  __shared__ __align__(16) float As[2][BK8][TM];
+  __shared__ __align__(16) float Bs[2][BK8][TN];
+  const int batch = blockIdx.z;
+  A += (long)batch * sA;
+  B += (long)batch * sB;
+  C += (long)batch * sC;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float ra[RA][4], rb[RB][4];
+
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < RA; ++r) {
+      const int q = tid + r * NT;
+      ra[r][0] = ra[r][1] = ra[r][2] = ra[r][3] = 0.f;
+      if (q < QA) {
+        if (!TA) {   // A[m][k]: TM rows x 2 quads
+          const int m = q >> 1, kk = (q & 1) * 4;
+          if ((m0 + m) < M) {
+            load_quad<AT>(A + (long)(m0 + m) * lda + k0 + kk, K - (k0 + kk), vec, ra[r]);
+            if (a_shift) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (k0 + kk + i < K) ra[r][i] -= a_shift[k0 + kk + i];
+            }
+          }
+        } else {     // A stored [k][m]
+          const int kk = q / (TM / 4), mm = (q % (TM / 4)) * 4;
+          if ((k0 + kk) < K) load_quad<AT>(A + (long)(k0 + kk) * lda + m0 + mm, M - (m0 + mm), vec, ra[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int q = tid + r * NT;
+      rb[r][0] = rb[r][1] = rb[r][2] = rb[r][3] = 0.f;
+      if (q < QB) {
+        if (!TB) {   // B[k][n]
+          const int kk = q / (TN / 4), nn = (q % (TN / 4)) * 4;
+          if ((k0 + kk) < K) load_quad<float>(B + (long)(k0 + kk) * ldb + n0 + nn, N - (n0 + nn), vec, rb[r]);
+        } else {     // B stored [n][k]
+          const int n = q >> 1, kk = (q & 1) * 4;
+          if ((n0 + n) < N) load_quad<float>(B + (long)(n0 + n) * ldb + k0 + kk, K - (k0 + kk), vec, rb[r]);
+        }
+      }
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < RA; ++r) {
+      const int q = tid + r * NT;
+      if (q < QA) {
+        if (!TA) {
+          const int m = q >> 1, kk = (q & 1) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) As[buf][kk + i][m] = ra[r][i];
+        } else {
+          const int kk = q / (TM / 4), mm = (q % (TM / 4)) * 4;
+          *reinterpret_cast<float4*>(&As[buf][kk][mm]) = make_float4(ra[r][0], ra[r][1], ra[r][2], ra[r][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int q = tid + r * NT;
+      if (q < QB) {
+        if (!TB) {
+          const int kk = q / (TN / 4), nn = (q % (TN / 4)) * 4;
+          *reinterpret_cast<float4*>(&Bs[buf][kk][nn]) = make_float4(rb[r][0], rb[r][1], rb[r][2], rb[r][3]);
+        } else {
+          const int n = q >> 1, kk = (q & 1) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) Bs[buf][kk + i][n] = rb[r][i];
+        }
+      }
+    }
+  };
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += BK8) {
+    const bool more = (k0 + BK8) < K;
+    if (more) fetch(k0 + BK8);                    // global loads in flight during the FMAs below
+#pragma unroll
+    for (int kk = 0; kk < BK8; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][TM / 2 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][TN / 2 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  float scale = alpha;
+  if (alpha_dev) scale *= *alpha_dev;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : TM / 2 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : TN / 2 + tx * 4 + (j - 4));
       if (n >= N) continue;
       float* dst = C + (long)m * ldc + n;
       const float prev = (beta != 0.f) ? beta * (*dst) : 0.f;
@@ -262,11 +404,40 @@ static int launch_sgemm_tile(int M, int N, int K, const void* A, int lda, long s
   return 0;
 }
 
+static inline int pick_tile8(int extent) {
+  const int w104 = (extent + 103) / 104 * 104, w128 = (extent + 127) / 128 * 128;
+  return w104 < w128 ? 104 : 128;
+}
+
+template <bool TA, bool TB, typename AT, int TM, int TN>
+static int launch_sgemm8_tile(int M, int N, int K, const void* A, int lda, long sA,
+                              const float* a_shift, const float* B, int ldb, long sB, float* C,
+                              int ldc, long sC, int batch, float alpha, const float* alpha_dev,
+                              float beta, cudaStream_t st) {
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, batch);
+  const bool vec = !(lda & 3) && !(ldb & 3) && !(sA & 3) && !(sB & 3) &&
+                   !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(B) & 15);
+  sgemm8_kernel<TA, TB, AT, TM, TN><<<grid, (TM / 8) * (TN / 8), 0, st>>>(
+      M, N, K, (const AT*)A, lda, sA, a_shift, B, ldb, sB, C, ldc, sC, alpha, alpha_dev, beta, vec);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
 template <bool TA, bool TB, typename AT>
 static int launch_sgemm_type(int M, int N, int K, const void* A, int lda, long sA,
                              const float* a_shift, const float* B, int ldb, long sB, float* C,
                              int ldc, long sC, int batch, float alpha, const float* alpha_dev,
                              float beta, cudaStream_t st) {
+  static const bool small_only = getenv("BASD_SGEMM_SMALL") != nullptr;   // A/B aid
+  if (!small_only && M >= 96 && N >= 96) {
+    const int tm8 = pick_tile8(M), tn8 = pick_tile8(N);
+#define BASD_ARGS8 M, N, K, A, lda, sA, a_shift, B, ldb, sB, C, ldc, sC, batch, alpha, alpha_dev, beta, st
+    if (tm8 == 104 && tn8 == 104) return launch_sgemm8_tile<TA, TB, AT, 104, 104>(BASD_ARGS8);
+    if (tm8 == 104) return launch_sgemm8_tile<TA, TB, AT, 104, 128>(BASD_ARGS8);
+    if (tn8 == 104) return launch_sgemm8_tile<TA, TB, AT, 128, 104>(BASD_ARGS8);
+    return launch_sgemm8_tile<TA, TB, AT, 128, 128>(BASD_ARGS8);
+#undef BASD_ARGS8
+  }
   const int tm = pick_tile(M), tn = pick_tile(N);
 #define BASD_ARGS M, N, K, A, lda, sA, a_shift, B, ldb, sB, C, ldc, sC, batch, alpha, alpha_dev, beta, st
   if (tm == 68 && tn == 68) return launch_sgemm_tile<TA, TB, AT, 68, 68>(BASD_ARGS);
