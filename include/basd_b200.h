@@ -150,6 +150,21 @@ int basd_weight_grad(const void* const* teacher_layers, int L, int E, const floa
                      int D, float gw_scale, const float* gw_scale_dev, float* partial,
                      float* d_weights, void* stream);
 
+/* ---- tensor-core batched GEMM (gemm_tc3.cu) ----------------------------------------- */
+
+/* C[b] (M x N, pitch ldc) = alpha * alpha_dev[0] * op(A[b]) op(B[b]) on tcgen05 tensor cores
+ * with fp32-level accuracy: every operand is split into two TF32 terms and three
+ * kind::tf32 MMAs per K step accumulate in TMEM ("3xTF32").  ta = 0: A stored M x K,
+ * ta = 1: stored K x M;  tb = 0: B stored K x N, tb = 1: stored N x K.  Pointers 16-byte
+ * aligned; M, N, K, pitches and strides multiples of 4 (basd_gemm_tc3_supported tells).
+ * Replaces torch.bmm (relational.py:47) and the matmuls of linalg.svd's backward for the
+ * per-sample Procrustes products. */
+int basd_gemm_tc3_supported(int M, int N, int K, int lda, int ldb, int ldc, long sa, long sb,
+                            long sc);
+int basd_gemm_tc3_batched(int ta, int tb, int M, int N, int K, const float* A, int lda, long sa,
+                          const float* B, int ldb, long sb, float* C, int ldc, long sc, int batch,
+                          float alpha, const float* alpha_dev, void* stream);
+
 /* ---- Procrustes glue (procrustes.cu) ------------------------------------------------ */
 
 /* out = sqrt(w) * (X - sum_n w_n X_n) per sample.                 (relational.py:36-43) */
@@ -157,15 +172,31 @@ int basd_weighted_center(const void* X, int dtype, long stride_x, const float* W
                          int N, int D, float* out, long stride_o, int batch, void* stream);
 int basd_extract_diag(const float* K, int N, int ld, long stride, int batch, float* diag,
                       void* stream);
-int basd_procrustes_rows_finish(float* rows2, float* Ut, int N, int ld, long stride, int batch,
-                                float rel_floor, float* sig, float* nuc, void* stream);
-int basd_procrustes_grad_prep(float* YA, float* YB, const float* FAt, const float* FBt, int N,
-                              int ld, long stride, int batch, const float* sig, const float* nuc,
-                              const float* ks, const float* kt, const float* w,
-                              const float* totals, float* f_out, float* gw, int with_grad,
-                              void* stream);
-/* geo_terms[i] = mean_b f[i,b], geo = mean_i geo_terms[i].  (relational.py:50, combined.py:76) */
-int basd_geo_reduce(const float* f, int E, int B, float* geo_terms, float* geo, void* stream);
+/* rows2 (rq x rq): row j = sigma_j q_j^T, Pt (rq x rp): unit rows p_j^T.  sig = row norms of
+ * rows2, nuc = their sum, keep_j = sig_j > rel_floor * max; rows2_j <- keep q_j^T sig^(eq/2),
+ * Pt_j <- keep p_j^T sig^(ep/2), pic_j = keep sig^(-(eq+ep)/2); eq, ep in {-1,0,1}.
+ * (the singular values / vectors torch.linalg.matrix_norm(ord="nuc") differentiates through,
+ * relational.py:48) */
+int basd_procrustes_rows_finish(float* rows2, int rq, int ldr, long stride_r, float* Pt, int rp,
+                                int ldp, long stride_p, int batch, float rel_floor, int eq, int ep,
+                                float* sig, float* nuc, float* pic, void* stream);
+/* f = tr_s + tr_t - 2 nuc, gw = df/dw~ from the images IA, IB (rq x N); a non-null Y (N x N,
+ * Gram side) becomes 2 diag(sqrt w)(I - Y) in place.                   (relational.py:34-50) */
+int basd_procrustes_grad_prep(float* YA, float* YB, const float* IA, const float* IB, int N, int rq,
+                              int ldi, long stride_i, int ldy, long stride_y, int batch,
+                              const float* pic, const float* nuc, const float* ks, const float* kt,
+                              const float* w, const float* totals, float* f_out, float* gw,
+                              int with_grad, void* stream);
+/* direct side (D <= N): T (N x D) <- 2 sqrt(w_n) (A - T). */
+int basd_procrustes_direct_grad(const float* A, float* T, const float* w, int N, int D, int batch,
+                                void* stream);
+/* dst (dtype) = alpha * alpha_dev[0] * src (fp32). */
+int basd_scale_out(const float* src, void* dst, int dtype, long n, float alpha,
+                   const float* alpha_dev, void* stream);
+/* geo_terms[i] = mean_b f[i,b], geo = mean_i geo_terms[i]  (relational.py:50, combined.py:76);
+ * NaN when any of the n_weights mixing weights is not finite (layer_selector.py:105, k = 0). */
+int basd_geo_reduce(const float* f, int E, int B, const float* weights, int n_weights,
+                    float* geo_terms, float* geo, void* stream);
 int basd_cast_out(const float* src, void* dst, int dtype, long n, void* stream);
 
 #ifdef __cplusplus

@@ -172,7 +172,7 @@ def mix_importance(weights_row, rows_stack, n_student):
 
 
 # ------------------------------------------------------------------ stage: Procrustes
-def pivoted_cholesky(k: torch.Tensor, rel_tol: float = 1e-6):
+def pivoted_cholesky(k: torch.Tensor, rel_tol: float = 1e-5):
     """Diagonally pivoted (rank-revealing) Cholesky of a PSD matrix, stopping when the
     largest remaining pivot drops below rel_tol * largest initial diagonal
     (kernel: procrustes_factor).  Returns L (N x N, zero columns beyond the rank) with
@@ -194,41 +194,59 @@ def pivoted_cholesky(k: torch.Tensor, rel_tol: float = 1e-6):
     return low
 
 
-def procrustes_sample(s_tok, t_tok, w, *, sv_floor: float = 1e-6, rel_tol: float = 1e-6):
+def procrustes_sample(s_tok, t_tok, w, *, sv_floor: float = 2.5e-4, rel_tol: float = 1e-5,
+                      direct_sv_floor: float = 1e-5):
     """One sample. s_tok (N,Ds), t_tok (N,Dt) fp32, w (N,) normalised.
     Returns value f = tr_s + tr_t - 2 nuc and the closed-form pieces of its gradient.
 
-    With K_s = A A^T = L_s L_s^T, K_t = B B^T = L_t L_t^T and X = L_s^T L_t = U S V^T the
-    singular values of the cross-covariance A^T B are those of X, and
-      d nuc/dA = Y_A A,  Y_A = (L_t V) S^+ (L_t V)^T ;   d nuc/dB = Y_B B,  Y_B = (L_s U) S^+ (L_s U)^T
-      diag(A polar(A^T B) B^T) = rowdot(L_s U, L_t V).
-    Only U comes out of the one-sided Jacobi sweep; V is recovered as the normalised rows
-    of U^T X (no inverse of any factor is ever formed)."""
+    Each side gets a factor F with F F^T = K (its N x N Gram):  when D <= N the weighted,
+    centred tokens themselves (F = A, r = D columns: no Gram, no squared condition number);
+    otherwise the pivoted-Cholesky factor of K (r = N).  X = F_s^T F_t (r_s x r_t) = U S V^T has
+    the singular values of the cross-covariance A^T B, and
+      d nuc/dA = Y_A A,  Y_A = (F_t V) S^+ (F_t V)^T ;   d nuc/dB = Y_B B,  Y_B = (F_s U) S^+ (F_s U)^T
+      diag(A polar(A^T B) B^T) = rowdot(F_s U, F_t V).
+    The one-sided Jacobi sweep orthogonalises the rows of the orientation of X with fewer
+    rows (r_q <= r_p) and yields the p-side vectors; the q-side ones are the normalised rows
+    of P^T X (no inverse of any factor is ever formed)."""
+    n = s_tok.shape[0]
     root = w.sqrt().unsqueeze(1)
     a = root * (s_tok - (w.unsqueeze(1) * s_tok).sum(0, keepdim=True))
     b = root * (t_tok - (w.unsqueeze(1) * t_tok).sum(0, keepdim=True))
-    k_s, k_t = a @ a.T, b @ b.T
-    l_s, l_t = pivoted_cholesky(k_s, rel_tol), pivoted_cholesky(k_t, rel_tol)
-    x = l_s.T @ l_t
-    # one-sided Jacobi on the columns of X^T would give V; we rotate columns of X^T ... the
-    # kernel orthogonalises the columns of G = X^T (so G R = V S, R = U):
-    u, sig, _ = torch.linalg.svd(x.double())
-    u, sig = u.float(), sig.float()
-    keep = sig > sv_floor * sig.max()
-    rows = u.T @ x                                        # S V^T, row i has norm sig_i
+    diag_s, diag_t = (a * a).sum(dim=1), (b * b).sum(dim=1)
+    direct_s, direct_t = a.shape[1] <= n, b.shape[1] <= n
+    f_s = a if direct_s else pivoted_cholesky(a @ a.T, rel_tol)
+    f_t = b if direct_t else pivoted_cholesky(b @ b.T, rel_tol)
+    floor = direct_sv_floor if (direct_s and direct_t) else sv_floor
+    swap = f_t.shape[1] > f_s.shape[1]                    # q = the side with fewer columns
+    f_p, f_q = (f_t, f_s) if swap else (f_s, f_t)
+    g = f_q.T @ f_p                                       # (r_q, r_p); rows -> sigma_j p_j^T
+    _, sig, pt = torch.linalg.svd(g.double(), full_matrices=False)
+    sig, pt = sig.float(), pt.float()                     # pt rows = p-side singular vectors
+    keep = sig > floor * sig.max()
+    rows = pt @ g.T                                       # S Q^T, row j has norm sig_j
     norms = rows.norm(dim=1)
-    vt = torch.where(keep.unsqueeze(1), rows / norms.clamp(min=1e-30).unsqueeze(1), torch.zeros_like(rows))
+    qt = torch.where(keep.unsqueeze(1), rows / norms.clamp(min=1e-30).unsqueeze(1), torch.zeros_like(rows))
     inv_sig = torch.where(keep, 1.0 / sig.clamp(min=1e-30), torch.zeros_like(sig))
     nuc = sig.sum()
-    f_a = l_t @ vt.T                                      # L_t V
-    f_b = (l_s @ u) * keep                                # L_s U
-    y_a = (f_a * inv_sig) @ f_a.T
-    y_b = (f_b * inv_sig) @ f_b.T
-    pi_diag = (f_b * f_a).sum(dim=1)
-    f = k_s.diagonal().sum() + k_t.diagonal().sum() - 2 * nuc
-    grad_s = 2 * root * (a - y_a @ a)                     # df/dS      (w held fixed)
-    grad_t = 2 * root * (b - y_b @ b)                     # df/dR'
-    grad_w = (k_s.diagonal() + k_t.diagonal() - 2 * pi_diag) / w   # df/dw (normalised w)
+    fq = f_q @ qt.T                                       # F_q Q   (N, r_q)
+    fp = (f_p @ pt.T) * keep                              # F_p P
+    pi_diag = (fp * fq).sum(dim=1)
+    f = diag_s.sum() + diag_t.sum() - 2 * nuc
+
+    def side_grad(tok, direct, mine, other, my_vecs):
+        """d nuc / d tok.  Direct side: (F_other W)(own D-space vectors)^T -- unit vectors only,
+        no 1/sigma.  Gram side: Y tok with Y = (F_other W) S^+ (F_other W)^T."""
+        if direct:
+            return other @ my_vecs
+        return ((other * inv_sig) @ other.T) @ tok
+
+    # p side: own vectors pt (rows), other-side image fq; q side: own vectors qt, image fp
+    d_p = side_grad(b if swap else a, direct_t if swap else direct_s, fp, fq, pt * keep.unsqueeze(1))
+    d_q = side_grad(a if swap else b, direct_s if swap else direct_t, fq, fp, qt)
+    d_a, d_b = (d_q, d_p) if swap else (d_p, d_q)
+    grad_s = 2 * root * (a - d_a)                         # df/dS      (w held fixed)
+    grad_t = 2 * root * (b - d_b)                         # df/dR'
+    grad_w = (diag_s + diag_t - 2 * pi_diag) / w          # df/dw (normalised w)
     return f, grad_s, grad_t, grad_w
 
 

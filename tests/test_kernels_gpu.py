@@ -37,6 +37,36 @@ def test_sgemm_all_layouts(ta, tb):
     assert (c.double() - ref).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(196, 196, 196), (196, 196, 384), (196, 768, 196), (128, 128, 256),
+                                   (68, 52, 36), (256, 320, 100), (192, 196, 256)])
+def test_gemm_tc3_matches_fp64_at_fp32_accuracy(ta, tb, m, n, k):
+    """tcgen05 3xTF32 batched GEMM: fp32-level accuracy (not TF32's 1e-3) against fp64,
+    and no worse than 4x the SIMT fp32 kernel's own error on the same inputs."""
+    eng = _eng()
+    torch.manual_seed(3)
+    b = 5
+    a = torch.randn(b, *((k, m) if ta else (m, k)), device=DEV) * torch.logspace(0, -3, m, device=DEV).view(
+        *((1, 1, m) if ta else (1, m, 1)))
+    bb = torch.randn(b, *((n, k) if tb else (k, n)), device=DEV)
+    alpha_dev = torch.tensor([0.5], device=DEV)
+    c = torch.full((b, m, n), float("nan"), device=DEV)
+    c_simt = torch.empty(b, m, n, device=DEV)
+    args = (ta, tb, m, n, k, a, a.shape[2], a[0].numel(), bb, bb.shape[2], bb[0].numel())
+    eng.sgemm(*args, c, n, m * n, b, alpha=2.0, alpha_dev=alpha_dev, tc=True)
+    eng.sgemm(*args, c_simt, n, m * n, b, alpha=2.0, alpha_dev=alpha_dev, tc=False)
+    ao = a.transpose(1, 2) if ta else a
+    bo = bb.transpose(1, 2) if tb else bb
+    ref = ao.double() @ bo.double()
+    scale = (ao.double().abs() @ bo.double().abs())           # sum |a||b| per output
+    err = ((c.double() - ref).abs() / scale).max()
+    err_simt = ((c_simt.double() - ref).abs() / scale).max()
+    assert torch.isfinite(c).all()
+    # worst case of the split: both operands carry 2^-22 after rounding lo, plus the dropped lo*lo
+    assert err < 1.5e-6, (float(err), float(err_simt))
+    assert err < 8 * err_simt + 1e-7, (float(err), float(err_simt))
+
+
 def test_sgemm_bf16_a_with_shift_and_shared_operand():
     eng = _eng()
     torch.manual_seed(1)

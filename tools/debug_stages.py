@@ -14,9 +14,10 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp(min=1e-300))
 
 
-def main(key="c1", batch=16, seed=5, temps=(0.2, 0.6, 1.0, 1.4)):
-    work = cs.workload(key, batch)
-    logits, targets, st, te, at = syn.make_inputs(work, seed=seed)
+def main(key="c1", batch=16, seed=5, temps=(0.2, 0.6, 1.0, 1.4), work=None, uniform_attn=None):
+    work = work if work is not None else cs.workload(key, batch)
+    kw = {} if uniform_attn is None else dict(uniform_attn=uniform_attn)
+    logits, targets, st, te, at = syn.make_inputs(work, seed=seed, **kw)
     proj_s, proj_t, logt0 = cs.selector_state(work)
     logt = torch.tensor(temps[:work.num_points]) if temps else logt0
     layers = sorted(st)
@@ -44,7 +45,8 @@ def main(key="c1", batch=16, seed=5, temps=(0.2, 0.6, 1.0, 1.4)):
         print("   |V^T V_model| diag min", float((v.T @ vm).diagonal().abs().min()),
               "orth err", float((v.T @ v - torch.eye(v.shape[0])).abs().max()))
     pro = eng.procrustes_forward(students, teachers, stats, sel.weights, work.n_student, True)
-    print("geo", float(pro.geo), "model", float(model["geo"]), "procrustes sweeps max", int(pro.sweeps.max()))
+    print("geo", float(pro.geo), "model", float(model["geo"]), "procrustes sweeps max", int(pro.sweeps.max()),
+          "mean", float(pro.sweeps.float().mean()), "hist", torch.bincount(pro.sweeps.cpu()).tolist())
     # backward with dL/dgeo = share_geo from the model
     ce, geo = model["ce"], model["geo"]
     share = (1 / geo) / (1 / ce + 1 / geo)

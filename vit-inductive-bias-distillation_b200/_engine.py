@@ -18,14 +18,19 @@ import torch.distributed as dist
 from . import _native as nat
 from ._native import call, ptr, stream
 
-JACOBI_TOL = 1e-6
-JACOBI_SWEEPS = 18
+import os as _os
+
+JACOBI_TOL = float(_os.environ.get("BASD_JACOBI_TOL", 1e-6))
+JACOBI_SWEEPS = int(_os.environ.get("BASD_JACOBI_SWEEPS", 18))
 CHOL_TOL = 1e-5          # pivoted-Cholesky rank cut (per-sample N x N Grams), relative to the
                          # largest diagonal: just above the fp32 accumulation noise of K
 GRAM_CHOL_TOL = 1e-7     # same for the D x D selector Grams
 SV_FLOOR = 1e-6          # k x k principal-angle SVD: directions below this are dropped
 ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerically zero in fp32
-PROC_SV_FLOOR = 2.5e-4   # Procrustes: below sqrt(eps) * sigma_max the recovered v_j is noise
+PROC_SV_FLOOR = 2.5e-4   # Procrustes with a Gram side: below sqrt(eps) * sigma_max the recovered v_j is noise
+# both sides direct (no Gram): q_j = normalise(G p_j) is recovered with noise ~eps*sqrt(K)*sigma_max/sigma_j;
+# measured on B200 (tools/debug_edge.py n256): 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
+PROC_SV_FLOOR_DIRECT = float(_os.environ.get("BASD_DIRECT_FLOOR", 3e-5))
 
 
 def _f32(*shape, device):
@@ -33,8 +38,23 @@ def _f32(*shape, device):
 
 
 # ---------------------------------------------------------------------------- op wrappers
+# the Procrustes products run on the tensor cores (3xTF32, gemm_tc3.cu) unless this is set
+# (A/B measurements and the SIMT-vs-tensor parity test)
+TC_GEMM = _os.environ.get("BASD_NO_TC_GEMM") is None
+
+
 def sgemm(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch=1, alpha=1.0,
-          alpha_dev=None, beta=0.0, a_shift=None):
+          alpha_dev=None, beta=0.0, a_shift=None, tc=False):
+    """C = alpha op(A) op(B) + beta C, batched.  `tc=True` asks for the tcgen05 3xTF32 kernel
+    (fp32 operands, beta = 0, 4-float aligned pitches); anything it does not accept runs on the
+    SIMT kernel."""
+    if (tc and TC_GEMM and beta == 0.0 and a_shift is None and a.dtype == torch.float32
+            and min(m, n) >= 32 and k >= 16 and batch <= 65535
+            and not ((a.data_ptr() | b.data_ptr() | c.data_ptr()) & 15)
+            and nat.load().basd_gemm_tc3_supported(m, n, k, lda, ldb, ldc, sa, sb, sc)):
+        call("basd_gemm_tc3_batched", int(ta), int(tb), m, n, k, ptr(a), lda, sa, ptr(b), ldb, sb,
+             ptr(c), ldc, sc, batch, float(alpha), ptr(alpha_dev), stream())
+        return
     call("basd_sgemm_batched", int(ta), int(tb), m, n, k, ptr(a), nat.dtype_code(a), lda, sa,
          ptr(a_shift), ptr(b), ldb, sb, ptr(c), ldc, sc, batch, float(alpha), ptr(alpha_dev),
          float(beta), stream())
@@ -268,8 +288,10 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
 class ProcrustesState:
     a: torch.Tensor           # (E,B,N,Ds) fp32 weighted-centred student tokens
     bm: torch.Tensor          # (E,B,N,Dt)
-    m_a: torch.Tensor | None  # (E*B,N,N)  2 sqrt(w) (I - Y_A)
+    m_a: torch.Tensor | None  # (E*B,N,N)  2 sqrt(w) (I - Y_A)      (Gram side: D > N)
     m_b: torch.Tensor | None
+    g_a: torch.Tensor | None  # (E*B,N,Ds) 2 sqrt(w) (A - (F_t V) U^T)   (direct side: D <= N)
+    g_b: torch.Tensor | None
     gw: torch.Tensor | None   # (E,B,N)    d f / d w~
     f: torch.Tensor           # (E*B,)
     geo_terms: torch.Tensor   # (E,)
@@ -277,6 +299,43 @@ class ProcrustesState:
     aligned: torch.Tensor     # (E,B,N,Dt) mixed + aligned teacher tokens
     w: torch.Tensor           # (E,B,N)
     sweeps: torch.Tensor | None = None
+
+
+class _Side:
+    """One side (student or teacher) of the per-sample Procrustes problems: the weighted,
+    centred tokens (p, N, D) and a factor F with F F^T = K = tok tok^T.  Gram side (D > N):
+    pivoted Cholesky of K, stored transposed (r = N rows of length N).  Direct side (D <= N):
+    F is the token matrix itself (r = D), no Gram and no squared condition number."""
+
+    def __init__(self, tok: torch.Tensor, n: int):
+        self.tok = tok
+        self.p, self.n, self.d = tok.shape
+        self.direct = self.d <= n
+        self.r = self.d if self.direct else n
+        dev = tok.device
+        self.diag = _f32(self.p, n, device=dev)
+        if self.direct:
+            call("basd_rowdot", ptr(tok), self.d, n * self.d, ptr(tok), self.d, n * self.d, n, self.d,
+                 self.p, ptr(self.diag), stream())
+            self.fac, self.ld = tok, self.d              # stored as F (N x r)
+        else:
+            k = _f32(self.p, n, n, device=dev)
+            sgemm(0, 1, n, n, self.d, tok, self.d, n * self.d, tok, self.d, n * self.d, k, n, n * n, self.p, tc=True)
+            call("basd_extract_diag", ptr(k), n, n, n * n, self.p, ptr(self.diag), stream())
+            self.fac = _f32(self.p, n, n, device=dev)    # stored as F^T (r x N)
+            pivoted_cholesky(k, self.fac, CHOL_TOL)
+            self.ld = n
+        self.stride = self.fac.shape[1] * self.fac.shape[2]
+
+    # operand descriptors for sgemm: (transpose flag, tensor, ld, stride)
+    def ft_left(self):        # F^T (r x N) as the left operand
+        return (1 if self.direct else 0), self.fac, self.ld, self.stride
+
+    def f_right(self):        # F (N x r) as the right operand
+        return (0 if self.direct else 1), self.fac, self.ld, self.stride
+
+    def ft_right(self):       # F^T (r x N) as the right operand
+        return (1 if self.direct else 0), self.fac, self.ld, self.stride
 
 
 def procrustes_forward(students, teachers, stats: Stats, weights, n_student, with_grad: bool):
@@ -303,53 +362,80 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
     call("basd_weighted_center", ptr(aligned), nat.dtype_code(aligned), n * d_t, ptr(w), n, n, d_t,
          ptr(bm), n * d_t, e * b, stream())
 
-    p, nn = e * b, n * n
-    ks = _f32(p, n, n, device=dev)
-    kt = _f32(p, n, n, device=dev)
-    sgemm(0, 1, n, n, d_s, a, d_s, n * d_s, a, d_s, n * d_s, ks, n, nn, p)
-    sgemm(0, 1, n, n, d_t, bm, d_t, n * d_t, bm, d_t, n * d_t, kt, n, nn, p)
-    ks_diag = _f32(p, n, device=dev)
-    kt_diag = _f32(p, n, device=dev)
-    call("basd_extract_diag", ptr(ks), n, n, nn, p, ptr(ks_diag), stream())
-    call("basd_extract_diag", ptr(kt), n, n, nn, p, ptr(kt_diag), stream())
-    ls_t = _f32(p, n, n, device=dev)
-    lt_t = _f32(p, n, n, device=dev)
-    pivoted_cholesky(ks, ls_t, CHOL_TOL)
-    pivoted_cholesky(kt, lt_t, CHOL_TOL)
-    x0, g = ks, kt                                       # Schur complements are dead: reuse
-    sgemm(0, 1, n, n, n, ls_t, n, nn, lt_t, n, nn, x0, n, nn, p)      # X   = L_s^T L_t
-    sgemm(0, 1, n, n, n, lt_t, n, nn, ls_t, n, nn, g, n, nn, p)       # X^T
+    p = e * b
+    side_s = _Side(a.view(p, n, d_s), n)
+    side_t = _Side(bm.view(p, n, d_t), n)
+    # q = the side with fewer factor columns: the Jacobi sweep orthogonalises the r_q rows of
+    # G = F_q^T F_p (length r_p >= r_q).  Ties keep q = teacher.
+    swap = side_t.r > side_s.r
+    sq, sp = (side_s, side_t) if swap else (side_t, side_s)
+    rq, rp = sq.r, sp.r
+    g = _f32(p, rq, rp, device=dev)
+    ta, fa_, lda, sa = sq.ft_left()
+    tb, fb_, ldb, sb = sp.f_right()
+    sgemm(ta, tb, rq, rp, n, fa_, lda, sa, fb_, ldb, sb, g, rp, rq * rp, p, tc=True)       # G = F_q^T F_p
+    g0 = _f32(p, rq, rp, device=dev)
+    g0.copy_(g)
     sweeps = torch.zeros(p, dtype=torch.int32, device=dev)
-    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes")  # rows -> sigma_j u_j^T
+    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes")  # rows -> sigma_j p_j^T
     rows_normalize(g, g, None, sort=False, square=False, rel_floor=ROW_FLOOR)
-    ut = g
-    rows2 = _f32(p, n, n, device=dev)
-    sgemm(0, 0, n, n, n, ut, n, nn, x0, n, nn, rows2, n, nn, p)        # U^T X = S V^T
-    sig = _f32(p, n, device=dev)
+    pt = g                                                                # (rq, rp) unit rows
+    rows2 = _f32(p, rq, rq, device=dev)
+    sgemm(0, 1, rq, rq, rp, pt, rp, rq * rp, g0, rp, rq * rp, rows2, rq, rq * rq, p, tc=True)  # P^T G^T = S Q^T
+    del g0
+    # scaling exponents (in halves) of the own-vector rows, see basd_procrustes_rows_finish
+    e_s = -1 if not side_t.direct else 0
+    e_t = -1 if not side_s.direct else 0
+    if side_s.direct and not side_t.direct:
+        e_t = 1
+    if side_t.direct and not side_s.direct:
+        e_s = 1
+    eq, ep = (e_s, e_t) if swap else (e_t, e_s)
+    floor = PROC_SV_FLOOR_DIRECT if (side_s.direct and side_t.direct) else PROC_SV_FLOOR
+    sig = _f32(p, rq, device=dev)
+    pic = _f32(p, rq, device=dev)
     nuc = _f32(p, device=dev)
-    call("basd_procrustes_rows_finish", ptr(rows2), ptr(ut), n, n, nn, p, PROC_SV_FLOOR, ptr(sig),
-         ptr(nuc), stream())
+    call("basd_procrustes_rows_finish", ptr(rows2), rq, rq, rq * rq, ptr(pt), rp, rp, rq * rp, p,
+         floor, eq, ep, ptr(sig), ptr(nuc), ptr(pic), stream())
     f = _f32(p, device=dev)
-    m_a = m_b = gw = None
+    m_a = m_b = g_a = g_b = gw = None
     if with_grad:
-        fa_t = x0                                        # reuse
-        fb_t = _f32(p, n, n, device=dev)
-        sgemm(0, 0, n, n, n, rows2, n, nn, lt_t, n, nn, fa_t, n, nn, p)   # (L_t v'_j)^T rows
-        sgemm(0, 0, n, n, n, ut, n, nn, ls_t, n, nn, fb_t, n, nn, p)      # (L_s u'_j)^T rows
-        m_a, m_b = ls_t, lt_t                            # reuse
-        sgemm(1, 0, n, n, n, fa_t, n, nn, fa_t, n, nn, m_a, n, nn, p)     # Y_A
-        sgemm(1, 0, n, n, n, fb_t, n, nn, fb_t, n, nn, m_b, n, nn, p)     # Y_B
+        img_q = _f32(p, rq, n, device=dev)                # rows (F_q q_j)^T (scaled)
+        img_p = _f32(p, rq, n, device=dev)                # rows (F_p p_j)^T (scaled)
+        tb, fb_, ldb, sb = sq.ft_right()
+        sgemm(0, tb, rq, n, rq, rows2, rq, rq * rq, fb_, ldb, sb, img_q, n, rq * n, p, tc=True)
+        tb, fb_, ldb, sb = sp.ft_right()
+        sgemm(0, tb, rq, n, rp, pt, rp, rq * rp, fb_, ldb, sb, img_p, n, rq * n, p, tc=True)
+
+        def side_operator(side, img_other, own, own_ld):
+            """Gram side: Y = I_o^T I_o (N x N).  Direct side: T = I_o^T own (N x D)."""
+            if side.direct:
+                t = _f32(p, n, side.d, device=dev)
+                sgemm(1, 0, n, side.d, rq, img_other, n, rq * n, own, own_ld, rq * own_ld, t,
+                      side.d, n * side.d, p, tc=True)
+                return None, t
+            y = _f32(p, n, n, device=dev)
+            sgemm(1, 0, n, n, rq, img_other, n, rq * n, img_other, n, rq * n, y, n, n * n, p, tc=True)
+            return y, None
+
+        y_p, t_p = side_operator(sp, img_q, pt, rp)
+        y_q, t_q = side_operator(sq, img_p, rows2, rq)
+        (m_a, g_a), (m_b, g_b) = ((y_q, t_q), (y_p, t_p)) if swap else ((y_p, t_p), (y_q, t_q))
         gw = _f32(e, b, n, device=dev)
-        call("basd_procrustes_grad_prep", ptr(m_a), ptr(m_b), ptr(fa_t), ptr(fb_t), n, n, nn, p,
-             ptr(sig), ptr(nuc), ptr(ks_diag), ptr(kt_diag), ptr(w), ptr(totals), ptr(f), ptr(gw),
-             1, stream())
+        call("basd_procrustes_grad_prep", ptr(m_a), ptr(m_b), ptr(img_q), ptr(img_p), n, rq, n, rq * n,
+             n, n * n, p, ptr(pic), ptr(nuc), ptr(side_s.diag), ptr(side_t.diag), ptr(w), ptr(totals),
+             ptr(f), ptr(gw), 1, stream())
+        if g_a is not None:
+            call("basd_procrustes_direct_grad", ptr(side_s.tok), ptr(g_a), ptr(w), n, d_s, p, stream())
+        if g_b is not None:
+            call("basd_procrustes_direct_grad", ptr(side_t.tok), ptr(g_b), ptr(w), n, d_t, p, stream())
     else:
-        call("basd_procrustes_grad_prep", None, None, None, None, n, n, nn, p, ptr(sig), ptr(nuc),
-             ptr(ks_diag), ptr(kt_diag), ptr(w), ptr(totals), ptr(f), None, 0, stream())
+        call("basd_procrustes_grad_prep", None, None, None, None, n, rq, n, rq * n, n, n * n, p, None,
+             ptr(nuc), ptr(side_s.diag), ptr(side_t.diag), ptr(w), ptr(totals), ptr(f), None, 0, stream())
     geo_terms = _f32(e, device=dev)
     geo = _f32((), device=dev)
-    call("basd_geo_reduce", ptr(f), e, b, ptr(geo_terms), ptr(geo), stream())
-    return ProcrustesState(a, bm, m_a, m_b, gw, f, geo_terms, geo, aligned, w, sweeps)
+    call("basd_geo_reduce", ptr(f), e, b, ptr(weights), e * l, ptr(geo_terms), ptr(geo), stream())
+    return ProcrustesState(a, bm, m_a, m_b, g_a, g_b, gw, f, geo_terms, geo, aligned, w, sweeps)
 
 
 def procrustes_backward(students, teachers, stats: Stats, pro: ProcrustesState,
@@ -364,12 +450,25 @@ def procrustes_backward(students, teachers, stats: Stats, pro: ProcrustesState,
     p, nn = e * b, n * n
     go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
     scale = 1.0 / (e * b)                                # d geo / d f_{i,b}
-    grad_s = _f32(e, b, n, d_s, device=dev)
-    sgemm(0, 0, n, d_s, n, pro.m_a, n, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
-          alpha=scale, alpha_dev=go)
+    if pro.m_a is not None:
+        grad_s = _f32(e, b, n, d_s, device=dev)
+        sgemm(0, 0, n, d_s, n, pro.m_a, n, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
+              alpha=scale, alpha_dev=go, tc=True)
+        outs = [_cast_like(grad_s[i], s) for i, s in enumerate(students)]
+    else:
+        g_a = pro.g_a.view(e, b, n, d_s)
+        outs = []
+        for i, s in enumerate(students):
+            out = torch.empty(s.shape, dtype=s.dtype, device=dev)
+            call("basd_scale_out", ptr(g_a[i]), ptr(out), nat.dtype_code(out), out.numel(), scale,
+                 ptr(go), stream())
+            outs.append(out)
     z = _f32(e, b, n, d_t, device=dev)
-    sgemm(0, 0, n, d_t, n, pro.m_b, n, nn, pro.bm, d_t, n * d_t, z, d_t, n * d_t, p,
-          alpha=scale, alpha_dev=go)
+    if pro.m_b is not None:
+        sgemm(0, 0, n, d_t, n, pro.m_b, n, nn, pro.bm, d_t, n * d_t, z, d_t, n * d_t, p,
+              alpha=scale, alpha_dev=go, tc=True)
+    else:
+        call("basd_scale_out", ptr(pro.g_b), ptr(z), nat.F32, z.numel(), scale, ptr(go), stream())
     # mixing-weight gradients: one pass over the teacher stack
     slices = nat.load().basd_weight_grad_slices()
     partial = _f32(slices * l * e, device=dev)
@@ -378,7 +477,6 @@ def procrustes_backward(students, teachers, stats: Stats, pro: ProcrustesState,
     call("basd_weight_grad", tptrs, l, e, ptr(z), ptr(pro.gw), ptr(stats.rows),
          nat.dtype_code(teachers[0]), b, n_t, n, d_t, scale, ptr(go), ptr(partial), ptr(d_weights),
          stream())
-    outs = [_cast_like(grad_s[i], s) for i, s in enumerate(students)]
     return outs, d_weights, (z if want_teacher_grad else None)
 
 

@@ -47,9 +47,14 @@ _SIG = {
     "basd_weight_grad": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],
     "basd_weighted_center": [_p, _i, _l, _p, _l, _i, _i, _p, _l, _i, _p],
     "basd_extract_diag": [_p, _i, _i, _l, _i, _p, _p],
-    "basd_procrustes_rows_finish": [_p, _p, _i, _i, _l, _i, _f, _p, _p, _p],
-    "basd_procrustes_grad_prep": [_p, _p, _p, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
-    "basd_geo_reduce": [_p, _i, _i, _p, _p, _p],
+    "basd_procrustes_rows_finish": [_p, _i, _i, _l, _p, _i, _i, _l, _i, _f, _i, _i, _p, _p, _p, _p],
+    "basd_procrustes_grad_prep": [_p, _p, _p, _p, _i, _i, _i, _l, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p,
+                                  _p, _i, _p],
+    "basd_procrustes_direct_grad": [_p, _p, _p, _i, _i, _i, _p],
+    "basd_scale_out": [_p, _p, _i, _l, _f, _p, _p],
+    "basd_geo_reduce": [_p, _i, _i, _p, _i, _p, _p, _p],
+    "basd_gemm_tc3_supported": [_i, _i, _i, _i, _i, _i, _l, _l, _l],
+    "basd_gemm_tc3_batched": [_i, _i, _i, _i, _i, _p, _i, _l, _p, _i, _l, _p, _i, _l, _i, _f, _p, _p],
     "basd_cast_out": [_p, _p, _i, _l, _p],
 }
 _RET = {"basd_token_gram_simt_workspace_floats": _l}

@@ -517,19 +517,35 @@ __device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, floa
   for (int o = LP >> 1; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);
   if (!valid) return;
   const bool rot = (ga * ga > tol2 * nx * ny) && nx > zero_thr && ny > zero_thr;   // group-uniform
-  float c = 1.f, sn = 0.f, t = 0.f;
+  float c = 1.f, sn = 0.f;
   if (rot) {
     ++nrot;
     worst = fmaxf(worst, __fdividef(ga * ga, nx * ny));
     const float d = ny - nx;
     const float h = fmaf(d, d, 4.f * ga * ga);
     const float root = h * rsqrtf(h);
-    t = __fdividef(2.f * fabsf(ga), fabsf(d) + root);
+    float t = __fdividef(2.f * fabsf(ga), fabsf(d) + root);
     t = ((d < 0.f) != (ga < 0.f)) ? -t : t;
     const float w2 = fmaf(t, t, 1.f);
     c = rsqrtf(w2);
     c = c * fmaf(-0.5f * w2, c * c, 1.5f);
     sn = c * t;
+    // New squared norms (the rows trade places below, so they swap as well).  The larger row
+    // grows by |t g| (no cancellation); the analytic update of the smaller one, a - |t g|,
+    // cancels when the rotation nearly annihilates it (graded matrices: a row 1e-4 of its partner
+    // would keep a norm of pure rounding noise and every later angle it takes part in would be
+    // wrong).  The 2x2 Gram determinant a_pp a_qq - g^2 is invariant under the rotation, so the
+    // smaller norm is det / larger -- accurate unless the rows are parallel.
+    const float tg = t * ga;                               // sign(tg) = sign(d)
+    const float big = (d >= 0.f) ? ny + tg : nx - tg;
+    const float r = __fdividef(1.f, big);
+    const float small = fmaxf(fmaf(nx, ny * r, -(ga * r) * ga), 0.f);
+    nx = (d >= 0.f) ? big : small;                         // x will hold y'
+    ny = (d >= 0.f) ? small : big;                         // y will hold x'
+  } else {
+    const float tmp = nx;
+    nx = ny;
+    ny = tmp;
   }
   // x' = c x - s y, y' = s x + c y, then the rows trade places: x <- y', y <- x'
 #pragma unroll
@@ -540,9 +556,6 @@ __device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, floa
     x[v].z = fmaf(sn, a.z, c * b.z); y[v].z = fmaf(c, a.z, -sn * b.z);
     x[v].w = fmaf(sn, a.w, c * b.w); y[v].w = fmaf(c, a.w, -sn * b.w);
   }
-  const float nxp = fmaxf(fmaf(-t, ga, nx), 0.f), nyp = fmaxf(fmaf(t, ga, ny), 0.f);
-  nx = nyp;
-  ny = nxp;
 }
 
 template <int LP, int NV, int MAXT>

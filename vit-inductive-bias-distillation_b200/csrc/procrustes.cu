@@ -3,11 +3,12 @@
 // (N x N Grams, factor products) runs in gemm_*.cu, the factorisations in jacobi.cu.
 //
 // Per sample:  A = sqrt(w)(S - mu_s), Bm = sqrt(w)(R' - mu_t)
-//   K_s = A A^T = L_s L_s^T, K_t = Bm Bm^T = L_t L_t^T, X = L_s^T L_t = U S V^T
-//   f = tr K_s + tr K_t - 2 sum(S)
-//   df/dS  = 2 sqrt(w) (I - Y_A) A,   Y_A = (L_t V) S^+ (L_t V)^T
-//   df/dR' = 2 sqrt(w) (I - Y_B) Bm,  Y_B = (L_s U) S^+ (L_s U)^T
-//   df/dw_n = (K_s[n,n] + K_t[n,n] - 2 [L_s U (L_t V)^T]_{nn}) / w_n
+//   each side has a factor F with F F^T = K (its N x N Gram): the pivoted-Cholesky factor of K
+//   when D > N ("Gram side", r = N columns), the tokens themselves when D <= N ("direct side",
+//   r = D).  X = F_s^T F_t = U S V^T,  f = tr K_s + tr K_t - 2 sum(S)
+//   Gram side:   df/dS = 2 sqrt(w) (I - Y_A) A,   Y_A = (F_t V) S^+ (F_t V)^T
+//   direct side: df/dS = 2 sqrt(w) (A - (F_t V) U^T)        (unit vectors only, no 1/sigma)
+//   df/dw_n = (K_s[n,n] + K_t[n,n] - 2 [F_s U (F_t V)^T]_{nn}) / w_n
 #include "common.cuh"
 
 namespace basd {
@@ -45,57 +46,70 @@ __global__ void extract_diag_kernel(const float* __restrict__ K, int N, int ld, 
     diag[(long)s * N + n] = K[(long)s * stride + (long)n * ld + n];
 }
 
-// rows2 (N x N) = U^T X, row j = sigma_j v_j^T.  Produces per sample:
-//   sig[j] = |row j| (refined singular values), nuc = sum_j sig[j]
-//   Vt'[j,:] = keep_j * row_j / sig_j^{3/2}      (i.e. v_j^T / sqrt(sig_j))
-//   Ut'[j,:] = keep_j * Ut[j,:] / sqrt(sig_j)
-// keep_j = sig_j > rel_floor * max(sig).
+// rows2 (rq x rq) = P^T X: row j = sigma_j q_j^T;  Pt (rq x rp): row j = p_j^T (unit).
+// Produces per sample:
+//   sig[j] = |rows2_j| (refined singular values), nuc = sum_j sig[j], keep_j = sig_j > rel_floor * max(sig)
+//   rows2[j,:] <- keep_j * q_j^T * sig_j^(eq/2)        Pt[j,:] <- keep_j * p_j^T * sig_j^(ep/2)
+//   pic[j]      = keep_j * sig_j^(-(eq+ep)/2)          (eq, ep in {-1, 0, +1})
+// so that images I = rows . F^T of the two sides recombine as  sum_j pic_j I_q[j,n] I_p[j,n].
+__device__ __forceinline__ float half_power(float sg, int e2) {
+  return e2 == 0 ? 1.f : (e2 < 0 ? rsqrtf(sg) : sqrtf(sg));
+}
+
 __global__ void __launch_bounds__(512)
-procrustes_rows_finish_kernel(float* __restrict__ rows2, float* __restrict__ Ut, int N, int ld,
-                              long stride, float rel_floor, float* __restrict__ sig,
-                              float* __restrict__ nuc) {
+procrustes_rows_finish_kernel(float* __restrict__ rows2, int rq, int ldr, long stride_r,
+                              float* __restrict__ Pt, int rp, int ldp, long stride_p,
+                              float rel_floor, int eq, int ep, float* __restrict__ sig,
+                              float* __restrict__ nuc, float* __restrict__ pic) {
   extern __shared__ float sm[];
-  float* nrm = sm;        // N
-  float* red = sm + N;    // 32
+  float* nrm = sm;        // rq
+  float* red = sm + rq;   // 32
   const int s = blockIdx.x;
-  float* R = rows2 + (long)s * stride;
-  float* U = Ut + (long)s * stride;
+  float* R = rows2 + (long)s * stride_r;
+  float* U = Pt + (long)s * stride_p;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int r = warp; r < N; r += nw) {
+  for (int r = warp; r < rq; r += nw) {
     float a = 0.f;
-    for (int c = lane; c < N; c += 32) { const float v = R[(long)r * ld + c]; a = fmaf(v, v, a); }
+    for (int c = lane; c < rq; c += 32) { const float v = R[(long)r * ldr + c]; a = fmaf(v, v, a); }
     a = warp_sum(a);
     if (lane == 0) nrm[r] = sqrtf(a);
   }
   __syncthreads();
   float mx = 0.f, tot = 0.f;
-  for (int r = threadIdx.x; r < N; r += blockDim.x) { mx = fmaxf(mx, nrm[r]); tot += nrm[r]; }
+  for (int r = threadIdx.x; r < rq; r += blockDim.x) { mx = fmaxf(mx, nrm[r]); tot += nrm[r]; }
   mx = block_max(mx, red);
   tot = block_sum(tot, red);
   const float floor_v = rel_floor * mx;
-  for (int r = warp; r < N; r += nw) {
+  for (int r = warp; r < rq; r += nw) {
     const float sg = nrm[r];
     const bool keep = sg > floor_v && sg > 0.f;
-    const float isq = keep ? rsqrtf(sg) : 0.f;
-    const float iv = keep ? isq / sg : 0.f;
-    for (int c = lane; c < N; c += 32) {
-      R[(long)r * ld + c] *= iv;
-      U[(long)r * ld + c] *= isq;
+    const float fq = keep ? half_power(sg, eq) / sg : 0.f;     // rows2_j / sig_j = q_j^T
+    const float fp = keep ? half_power(sg, ep) : 0.f;
+    for (int c = lane; c < rq; c += 32) R[(long)r * ldr + c] *= fq;
+    for (int c = lane; c < rp; c += 32) U[(long)r * ldp + c] *= fp;
+    if (lane == 0) {
+      sig[(long)s * rq + r] = sg;
+      if (pic) {
+        const int e2 = -(eq + ep);                             // pic = sig^(e2/2), e2 in [-2, 2]
+        const float h = half_power(sg, e2);
+        pic[(long)s * rq + r] = keep ? ((e2 == 2 || e2 == -2) ? h * h : h) : 0.f;
+      }
     }
-    if (lane == 0) sig[(long)s * N + r] = sg;
   }
   if (threadIdx.x == 0) nuc[s] = tot;
 }
 
-// Per sample, after Y_A = FAt'^T FAt', Y_B = FBt'^T FBt' (N x N each):
+// Per sample, with the images IA = rows2' . F_q^T and IB = Pt' . F_p^T (rq x N each):
 //   f = tr_s + tr_t - 2 nuc
-//   pi[n] = sum_j FBt'[j,n] FAt'[j,n] sig[j]
+//   pi[n] = sum_j pic[j] IA[j,n] IB[j,n]
 //   gw[n] = ((ks[n] + kt[n] - 2 pi[n]) / w[n] - f) / total        (d f / d w~)
-//   M_A = 2 diag(sqrt w) (I - Y_A)   (in place over Y_A), same for M_B.
+//   for a Gram side, Y (N x N, = I_other^T I_other) becomes M = 2 diag(sqrt w) (I - Y) in place;
+//   pass a null Y for a direct side.
 __global__ void __launch_bounds__(512)
 procrustes_grad_prep_kernel(float* __restrict__ YA, float* __restrict__ YB,
-                            const float* __restrict__ FAt, const float* __restrict__ FBt, int N,
-                            int ld, long stride, const float* __restrict__ sig,
+                            const float* __restrict__ IA, const float* __restrict__ IB, int N,
+                            int rq, int ldi, long stride_i, int ldy, long stride_y,
+                            const float* __restrict__ pic,
                             const float* __restrict__ nuc, const float* __restrict__ ks,
                             const float* __restrict__ kt, const float* __restrict__ w,
                             const float* __restrict__ totals, float* __restrict__ f_out,
@@ -110,36 +124,68 @@ procrustes_grad_prep_kernel(float* __restrict__ YA, float* __restrict__ YB,
   __syncthreads();
   if (!with_grad) return;
   const float f = f_sh;
-  const float* fa = FAt + (long)s * stride;
-  const float* fb = FBt + (long)s * stride;
+  const float* fa = IA + (long)s * stride_i;
+  const float* fb = IB + (long)s * stride_i;
   const float tot = totals[s];
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     float pi = 0.f;
-    for (int j = 0; j < N; ++j)
-      pi = fmaf(fb[(long)j * ld + n] * fa[(long)j * ld + n], sig[(long)s * N + j], pi);
+    for (int j = 0; j < rq; ++j)
+      pi = fmaf(fb[(long)j * ldi + n] * fa[(long)j * ldi + n], pic[(long)s * rq + j], pi);
     const float wn = w[(long)s * N + n];
     gw[(long)s * N + n] = ((ks[(long)s * N + n] + kt[(long)s * N + n] - 2.f * pi) / wn - f) / tot;
   }
-  float* ya = YA + (long)s * stride;
-  float* yb = YB + (long)s * stride;
+  float* ya = YA ? YA + (long)s * stride_y : nullptr;
+  float* yb = YB ? YB + (long)s * stride_y : nullptr;
+  if (!ya && !yb) return;
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
     const int r = e / N, c = e - r * N;
     const float sc = 2.f * sqrtf(w[(long)s * N + r]);
     const float id = (r == c) ? 1.f : 0.f;
-    ya[(long)r * ld + c] = sc * (id - ya[(long)r * ld + c]);
-    yb[(long)r * ld + c] = sc * (id - yb[(long)r * ld + c]);
+    if (ya) ya[(long)r * ldy + c] = sc * (id - ya[(long)r * ldy + c]);
+    if (yb) yb[(long)r * ldy + c] = sc * (id - yb[(long)r * ldy + c]);
   }
 }
 
+// Direct side: T (N x D, in/out) <- 2 sqrt(w_n) (A - T)  with T = I_other^T . own_vectors on entry.
+__global__ void __launch_bounds__(256)
+procrustes_direct_grad_kernel(const float* __restrict__ A, float* __restrict__ T,
+                              const float* __restrict__ w, int N, int D) {
+  const int s = blockIdx.y;
+  const long base = (long)s * N * D;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N * D;
+       e += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(e / D);
+    T[base + e] = 2.f * sqrtf(w[(long)s * N + n]) * (A[base + e] - T[base + e]);
+  }
+}
+
+// dst (token dtype) = alpha * alpha_dev[0] * src (fp32), elementwise.
+template <typename T>
+__global__ void scale_out_kernel(const float* __restrict__ src, T* __restrict__ dst, long n,
+                                 float alpha, const float* __restrict__ alpha_dev) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float sc = alpha_dev ? alpha * alpha_dev[0] : alpha;
+  if (i < n) dst[i] = from_f32<T>(sc * src[i]);
+}
+
 // geo_terms[i] = mean_b f[i,b]; geo = mean_i geo_terms[i]    (relational.py:50, combined.py:76)
+// A non-finite mixing weight (MP rank 0 -> 0/0 at layer_selector.py:105) poisons the mixed
+// tokens of the reference; fmax/fmin-style guards in the kernels in between would swallow the
+// NaN, so it is re-asserted here: the loss is NaN exactly when the reference's is.
 __global__ void geo_reduce_kernel(const float* __restrict__ f, int E, int B,
+                                  const float* __restrict__ weights, int n_weights,
                                   float* __restrict__ geo_terms, float* __restrict__ geo) {
   __shared__ float red[32];
+  float bad = 0.f;
+  for (int i = threadIdx.x; i < n_weights; i += blockDim.x)
+    if (!isfinite(weights[i])) bad = 1.f;
+  bad = block_max(bad, red);
   float total = 0.f;
   for (int i = 0; i < E; ++i) {
     float a = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) a += f[(long)i * B + b];
     a = block_sum(a, red) / (float)B;
+    if (bad > 0.f) a = __int_as_float(0x7fc00000);
     if (threadIdx.x == 0) geo_terms[i] = a;
     total += a;
     __syncthreads();
@@ -182,31 +228,57 @@ extern "C" int basd_extract_diag(const float* K, int N, int ld, long stride, int
   return 0;
 }
 
-extern "C" int basd_procrustes_rows_finish(float* rows2, float* Ut, int N, int ld, long stride,
-                                           int batch, float rel_floor, float* sig, float* nuc,
-                                           void* stream) {
+extern "C" int basd_procrustes_rows_finish(float* rows2, int rq, int ldr, long stride_r, float* Pt,
+                                           int rp, int ldp, long stride_p, int batch,
+                                           float rel_floor, int eq, int ep, float* sig, float* nuc,
+                                           float* pic, void* stream) {
   if (batch <= 0) return 0;
-  procrustes_rows_finish_kernel<<<batch, 512, (N + 32) * sizeof(float), ST>>>(
-      rows2, Ut, N, ld, stride, rel_floor, sig, nuc);
+  if (eq < -1 || eq > 1 || ep < -1 || ep > 1) return -2;
+  procrustes_rows_finish_kernel<<<batch, 512, (rq + 32) * sizeof(float), ST>>>(
+      rows2, rq, ldr, stride_r, Pt, rp, ldp, stride_p, rel_floor, eq, ep, sig, nuc, pic);
   BASD_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int basd_procrustes_grad_prep(float* YA, float* YB, const float* FAt, const float* FBt,
-                                         int N, int ld, long stride, int batch, const float* sig,
+extern "C" int basd_procrustes_grad_prep(float* YA, float* YB, const float* IA, const float* IB,
+                                         int N, int rq, int ldi, long stride_i, int ldy,
+                                         long stride_y, int batch, const float* pic,
                                          const float* nuc, const float* ks, const float* kt,
                                          const float* w, const float* totals, float* f_out,
                                          float* gw, int with_grad, void* stream) {
   if (batch <= 0) return 0;
-  procrustes_grad_prep_kernel<<<batch, 512, 0, ST>>>(YA, YB, FAt, FBt, N, ld, stride, sig, nuc, ks,
-                                                     kt, w, totals, f_out, gw, with_grad);
+  procrustes_grad_prep_kernel<<<batch, 512, 0, ST>>>(YA, YB, IA, IB, N, rq, ldi, stride_i, ldy,
+                                                     stride_y, pic, nuc, ks, kt, w, totals, f_out,
+                                                     gw, with_grad);
   BASD_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int basd_geo_reduce(const float* f, int E, int B, float* geo_terms, float* geo,
-                               void* stream) {
-  geo_reduce_kernel<<<1, 256, 0, ST>>>(f, E, B, geo_terms, geo);
+extern "C" int basd_procrustes_direct_grad(const float* A, float* T, const float* w, int N, int D,
+                                           int batch, void* stream) {
+  if (batch <= 0) return 0;
+  const long per = (long)N * D;
+  dim3 grid((unsigned)((per + 1023) / 1024), batch);
+  procrustes_direct_grad_kernel<<<grid, 256, 0, ST>>>(A, T, w, N, D);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_scale_out(const float* src, void* dst, int dtype, long n, float alpha,
+                              const float* alpha_dev, void* stream) {
+  if (n <= 0) return 0;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == BASD_DTYPE_BF16)
+    scale_out_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>(src, (__nv_bfloat16*)dst, n, alpha, alpha_dev);
+  else
+    scale_out_kernel<float><<<grid, 256, 0, ST>>>(src, (float*)dst, n, alpha, alpha_dev);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_geo_reduce(const float* f, int E, int B, const float* weights, int n_weights,
+                               float* geo_terms, float* geo, void* stream) {
+  geo_reduce_kernel<<<1, 256, 0, ST>>>(f, E, B, weights, weights ? n_weights : 0, geo_terms, geo);
   BASD_LAUNCH_CHECK();
   return 0;
 }
