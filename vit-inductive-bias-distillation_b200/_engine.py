@@ -22,6 +22,9 @@ import os as _os
 
 JACOBI_TOL = float(_os.environ.get("BASD_JACOBI_TOL", 1e-6))
 JACOBI_SWEEPS = int(_os.environ.get("BASD_JACOBI_SWEEPS", 18))
+# per-sample Procrustes SVDs: sigma is re-measured from P^T X (second-order accurate) and the polar
+# factor is insensitive to rotations inside clusters, so the sweep may stop one level earlier
+PROC_JACOBI_TOL = float(_os.environ.get("BASD_PROC_JACOBI_TOL", 1e-6))
 CHOL_TOL = 1e-5          # pivoted-Cholesky rank cut (per-sample N x N Grams), relative to the
                          # largest diagonal: just above the fp32 accumulation noise of K
 GRAM_CHOL_TOL = 1e-7     # same for the D x D selector Grams
@@ -88,16 +91,17 @@ def pivoted_cholesky(k, lt, rel_tol, dims=None, rank_out=None):
 jacobi_log = None
 
 
-def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi"):
+def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi", tol=None):
     batch, n, m = g.shape
+    tol = JACOBI_TOL if tol is None else tol
     if jacobi_log is not None:
         sweeps_out = sweeps_out if sweeps_out is not None else torch.zeros(batch, dtype=torch.int32, device=g.device)
         rot = torch.zeros(batch, dtype=torch.int32, device=g.device)
-        call("basd_jacobi_rows_counted", ptr(g), n, m, m, n * m, batch, ptr(dims), JACOBI_TOL,
+        call("basd_jacobi_rows_counted", ptr(g), n, m, m, n * m, batch, ptr(dims), tol,
              JACOBI_SWEEPS, ptr(sweeps_out), ptr(rot), stream())
         jacobi_log.append((tag, n, m, dims, sweeps_out, rot))
         return
-    call("basd_jacobi_rows", ptr(g), n, m, m, n * m, batch, ptr(dims), JACOBI_TOL, JACOBI_SWEEPS,
+    call("basd_jacobi_rows", ptr(g), n, m, m, n * m, batch, ptr(dims), tol, JACOBI_SWEEPS,
          ptr(sweeps_out), stream())
 
 
@@ -377,7 +381,7 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
     g0 = _f32(p, rq, rp, device=dev)
     g0.copy_(g)
     sweeps = torch.zeros(p, dtype=torch.int32, device=dev)
-    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes")  # rows -> sigma_j p_j^T
+    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes", tol=PROC_JACOBI_TOL)  # rows -> sigma_j p_j^T
     rows_normalize(g, g, None, sort=False, square=False, rel_floor=ROW_FLOOR)
     pt = g                                                                # (rq, rp) unit rows
     rows2 = _f32(p, rq, rq, device=dev)

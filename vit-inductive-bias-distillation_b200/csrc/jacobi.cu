@@ -503,10 +503,22 @@ jacobi_rows_grouped_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
 // pair has met exactly once (the odd-even transposition network).  Shared-memory traffic per pair
 // is half that of the round-robin kernel, which ncu showed to be shared-memory-bandwidth bound.
 // All reloads are unconditional so at most two rows are ever live in registers.
+// Rows are held as  row = d * stored  with a per-row scale d ("fast" / scaled rotations): the
+// plane rotation  x' = c x - s y, y' = s x + c y  becomes two FMAs per element pair on the stored
+// values,  stored_y' = stored_y + (t dx/dy) stored_x,  stored_x' = stored_x - (t dy/dx) stored_y,
+// with the cosine folded into the scales (d' = c d_partner) instead of two FMUL + two FFMA.
+// Scales shrink by c >= 1/sqrt(2) per rotation and are folded back into the rows every 16 steps.
+template <int NV>
+__device__ __forceinline__ void fold_scale(float4 (&r)[NV], float& d) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) { r[v].x *= d; r[v].y *= d; r[v].z *= d; r[v].w *= d; }
+  d = 1.f;
+}
+
 template <int LP, int NV>
-__device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, float4 (&y)[NV],
-                                                float& ny, bool valid, float tol2, float zero_thr,
-                                                float& worst, int& nrot) {
+__device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, float& dx,
+                                                float4 (&y)[NV], float& ny, float& dy, bool valid,
+                                                float tol2, float zero_thr, float& worst, int& nrot) {
   float ga = 0.f;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -516,8 +528,9 @@ __device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, floa
 #pragma unroll
   for (int o = LP >> 1; o > 0; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);
   if (!valid) return;
+  ga *= dx * dy;
   const bool rot = (ga * ga > tol2 * nx * ny) && nx > zero_thr && ny > zero_thr;   // group-uniform
-  float c = 1.f, sn = 0.f;
+  float c = 1.f, t1 = 0.f, t2 = 0.f;
   if (rot) {
     ++nrot;
     worst = fmaxf(worst, __fdividef(ga * ga, nx * ny));
@@ -529,7 +542,8 @@ __device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, floa
     const float w2 = fmaf(t, t, 1.f);
     c = rsqrtf(w2);
     c = c * fmaf(-0.5f * w2, c * c, 1.5f);
-    sn = c * t;
+    t1 = t * __fdividef(dx, dy);
+    t2 = t * __fdividef(dy, dx);
     // New squared norms (the rows trade places below, so they swap as well).  The larger row
     // grows by |t g| (no cancellation); the analytic update of the smaller one, a - |t g|,
     // cancels when the rotation nearly annihilates it (graded matrices: a row 1e-4 of its partner
@@ -547,15 +561,19 @@ __device__ __forceinline__ void rotate_and_swap(float4 (&x)[NV], float& nx, floa
     nx = ny;
     ny = tmp;
   }
-  // x' = c x - s y, y' = s x + c y, then the rows trade places: x <- y', y <- x'
+  // y' = s x + c y = (c dy)(stored_y + t1 stored_x),  x' = c x - s y = (c dx)(stored_x - t2 stored_y);
+  // then the rows trade places: x <- y', y <- x'
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const float4 a = x[v], b = y[v];
-    x[v].x = fmaf(sn, a.x, c * b.x); y[v].x = fmaf(c, a.x, -sn * b.x);
-    x[v].y = fmaf(sn, a.y, c * b.y); y[v].y = fmaf(c, a.y, -sn * b.y);
-    x[v].z = fmaf(sn, a.z, c * b.z); y[v].z = fmaf(c, a.z, -sn * b.z);
-    x[v].w = fmaf(sn, a.w, c * b.w); y[v].w = fmaf(c, a.w, -sn * b.w);
+    x[v].x = fmaf(t1, a.x, b.x); y[v].x = fmaf(-t2, b.x, a.x);
+    x[v].y = fmaf(t1, a.y, b.y); y[v].y = fmaf(-t2, b.y, a.y);
+    x[v].z = fmaf(t1, a.z, b.z); y[v].z = fmaf(-t2, b.z, a.z);
+    x[v].w = fmaf(t1, a.w, b.w); y[v].w = fmaf(-t2, b.w, a.w);
   }
+  const float ndx = c * dy;
+  dy = c * dx;
+  dx = ndx;
 }
 
 template <int LP, int NV, int MAXT>
@@ -580,7 +598,7 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
   float* xbuf = smem;                                    // (cap/2 + 1) rows of LP*NV quads
   const int pitch = LP * NV * 4;                         // every lane may touch all its NV quads
   const int cap = dims ? min(n, dim_hi) : n;             // largest problem this launch accepts
-  float* xn = smem + (size_t)((cap + 1) / 2 + 1) * pitch;  // squared norms of the parked rows
+  float2* xn = reinterpret_cast<float2*>(smem + (size_t)((cap + 1) / 2 + 1) * pitch);  // (squared norm, scale) of the parked rows
   (void)ldw;
   const int h = (nn + 1) >> 1;                           // groups; the last one has no right row if nn is odd
   const bool active = gid < h;
@@ -607,7 +625,10 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
   float4* my_slot = reinterpret_cast<float4*>(xbuf + (size_t)slot * pitch);
   float4* right_slot = reinterpret_cast<float4*>(xbuf + (size_t)min(gid + 1, spare) * pitch);
   int sweep = 0;
+  float da = 1.f, db = 1.f;                               // row = scale * stored (fast rotations)
   for (; sweep < max_sweeps && nn >= 2; ++sweep) {
+    fold_scale<NV>(a, da);
+    fold_scale<NV>(b, db);
     float na = 0.f, nb = 0.f;                             // refresh the carried norms
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -626,33 +647,39 @@ jacobi_rows_oddeven_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
     float worst = 0.f;
     for (int step = 0; step < nn; ++step) {
       if ((step & 1) == 0) {
-        rotate_and_swap<LP, NV>(a, na, b, nb, has_b, tol2, zero_thr, worst, nrot);
+        if ((step & 15) == 0 && step) { fold_scale<NV>(a, da); fold_scale<NV>(b, db); }
+        rotate_and_swap<LP, NV>(a, na, da, b, nb, db, has_b, tol2, zero_thr, worst, nrot);
       } else {
         // park the left row of every group; the left neighbour pairs it with its right row
 #pragma unroll
         for (int v = 0; v < NV; ++v) my_slot[gl + LP * v] = a[v];
-        if (gl == 0) xn[slot] = na;
+        if (gl == 0) xn[slot] = make_float2(na, da);
         __syncthreads();
         const bool pair_ok = has_b && (gid + 1 < h);
         float4 y[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) y[v] = right_slot[gl + LP * v];
-        float ny = xn[min(gid + 1, spare)];
-        rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst, nrot);
+        const float2 nd = xn[min(gid + 1, spare)];
+        float ny = nd.x, dy = nd.y;
+        rotate_and_swap<LP, NV>(b, nb, db, y, ny, dy, pair_ok, tol2, zero_thr, worst, nrot);
         if (pair_ok) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) right_slot[gl + LP * v] = y[v];
-          if (gl == 0) xn[gid + 1] = ny;
+          if (gl == 0) xn[gid + 1] = make_float2(ny, dy);
         }
         __syncthreads();
 #pragma unroll
         for (int v = 0; v < NV; ++v) a[v] = my_slot[gl + LP * v];
-        na = xn[slot];
+        const float2 mine = xn[slot];
+        na = mine.x;
+        da = mine.y;
       }
     }
     worst = block_max(worst, red_scratch);
     if (worst < tol) { ++sweep; break; }
   }
+  fold_scale<NV>(a, da);
+  fold_scale<NV>(b, db);
   if (active) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -709,7 +736,7 @@ jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, l
   const int mv = (mm + 3) >> 2;
   constexpr int pitch = LP * NV * 4;
   float* xbuf = smem;                                     // gpc + 1 parking slots
-  float* xn = smem + (size_t)(gpc + 1) * pitch;           // squared norms of the parked rows
+  float2* xn = reinterpret_cast<float2*>(smem + (size_t)(gpc + 1) * pitch);   // (squared norm, scale) of the parked rows
   const int h = (nn + 1) >> 1;
   const bool active = gid < h;
   const int row_a = 2 * gid, row_b = 2 * gid + 1;
@@ -731,10 +758,10 @@ jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, l
   }
   const float tol2 = tol * tol;
   float4* my_slot = reinterpret_cast<float4*>(xbuf + (size_t)lgid * pitch);
-  float* my_norm = xn + lgid;
+  float2* my_norm = xn + lgid;
   // right neighbour's parking slot: next group of this CTA, or slot 0 of the next CTA (DSMEM)
   float4* right_slot;
-  float* right_norm;
+  float2* right_norm;
   if (lgid + 1 < gpc) {
     right_slot = reinterpret_cast<float4*>(xbuf + (size_t)(lgid + 1) * pitch);
     right_norm = xn + lgid + 1;
@@ -747,9 +774,12 @@ jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, l
   }
   int* flag0 = cluster.map_shared_rank(cflag, 0);
   int sweep = 0;
+  float da = 1.f, db = 1.f;                               // row = scale * stored (fast rotations)
   for (; sweep < max_sweeps && nn >= 2; ++sweep) {
     if (crank == 0 && tid == 0) { cflag[0] = 0; cflag[1] = 0; }
     cluster.sync();
+    fold_scale<NV>(a, da);
+    fold_scale<NV>(b, db);
     float na = 0.f, nb = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -768,33 +798,39 @@ jacobi_rows_oe_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, l
     float worst = 0.f;
     for (int step = 0; step < nn; ++step) {
       if ((step & 1) == 0) {
-        rotate_and_swap<LP, NV>(a, na, b, nb, has_b, tol2, zero_thr, worst, nrot);
+        if ((step & 15) == 0 && step) { fold_scale<NV>(a, da); fold_scale<NV>(b, db); }
+        rotate_and_swap<LP, NV>(a, na, da, b, nb, db, has_b, tol2, zero_thr, worst, nrot);
       } else {
 #pragma unroll
         for (int v = 0; v < NV; ++v) my_slot[gl + LP * v] = a[v];
-        if (gl == 0) *my_norm = na;
+        if (gl == 0) *my_norm = make_float2(na, da);
         cluster.sync();
         const bool pair_ok = has_b && (gid + 1 < h);
         float4 y[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) y[v] = right_slot[gl + LP * v];
-        float ny = *right_norm;
-        rotate_and_swap<LP, NV>(b, nb, y, ny, pair_ok, tol2, zero_thr, worst, nrot);
+        const float2 nd = *right_norm;
+        float ny = nd.x, dy = nd.y;
+        rotate_and_swap<LP, NV>(b, nb, db, y, ny, dy, pair_ok, tol2, zero_thr, worst, nrot);
         if (pair_ok) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) right_slot[gl + LP * v] = y[v];
-          if (gl == 0) *right_norm = ny;
+          if (gl == 0) *right_norm = make_float2(ny, dy);
         }
         cluster.sync();
 #pragma unroll
         for (int v = 0; v < NV; ++v) a[v] = my_slot[gl + LP * v];
-        na = *my_norm;
+        const float2 mine = *my_norm;
+        na = mine.x;
+        da = mine.y;
       }
     }
     const float all_worst = cluster_max_nonneg(worst, cluster, flag0 + 1, red_scratch);
     cluster.sync();                                       // all have read before rank 0 resets
     if (all_worst < tol) { ++sweep; break; }
   }
+  fold_scale<NV>(a, da);
+  fold_scale<NV>(b, db);
   if (active) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -1075,7 +1111,7 @@ static int launch_oe_cluster(float* G, int n, int m, int ld, long stride, int ba
   int csize = 1;
   while (csize < 8 && csize * gpc * 2 < n) csize <<= 1;
   if (csize * gpc * 2 < n) return -12;                     // does not fit a portable cluster
-  const size_t dyn = ((size_t)(gpc + 1) * LP * NV * 4 + gpc + 2) * sizeof(float);
+  const size_t dyn = ((size_t)(gpc + 1) * LP * NV * 4 + 2 * (gpc + 2)) * sizeof(float);
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe_cluster_kernel<LP, NV, MAXT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
@@ -1101,7 +1137,7 @@ static int launch_oddeven(float* G, int n, int m, int ld, long stride, int batch
                           int dim_lo = 0, int dim_hi = 1 << 30, int* rot_out = nullptr) {
   const int cap = (dims && dim_hi < n) ? dim_hi : n;
   const size_t slots = (size_t)(cap + 1) / 2 + 1;
-  const size_t dyn = (slots * LP * NV * 4 + slots + 4) * sizeof(float);
+  const size_t dyn = (slots * LP * NV * 4 + 2 * slots + 4) * sizeof(float);
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oddeven_kernel<LP, NV, MAXT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   int threads = ((cap + 1) / 2) * LP;
