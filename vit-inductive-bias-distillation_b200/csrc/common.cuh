@@ -85,4 +85,10 @@ int launch_gram_reduce(const float* partial, int slices, int D, int tile, float*
 int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial /* >= 64*D floats */,
                        float* out, cudaStream_t st);
 
+// jacobi_oe8.cu: register-resident Jacobi with eight rows per 16-lane group (<= 224 x 224 active);
+// returns -100 when the shape does not fit.
+int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                      float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                      int dim_hi, int* rot_out);
+
 }  // namespace basd

@@ -1228,6 +1228,13 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
   const size_t need = ((size_t)n * quads * 4 + n) * sizeof(float);
   const bool legacy = getenv("BASD_JACOBI_LEGACY") != nullptr;   // A/B debugging aids
   const bool no_oddeven = getenv("BASD_JACOBI_ROUNDROBIN") != nullptr;
+  // eight rows per 16-lane group (jacobi_oe8.cu): a quarter of the shared-memory exchange traffic
+  static const bool no_oe8 = getenv("BASD_JACOBI_NO_OE8") != nullptr;
+  if (!legacy && !no_oddeven && !no_oe8 && n <= 224 && m <= 224) {
+    const int e = launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st,
+                                    0, 1 << 30, rot_out);
+    if (e != -100) return e;
+  }
   // register-resident odd-even kernel: every row pair needs its own group of 8 lanes
   if (!legacy && !no_oddeven && ((n + 1) / 2) * 8 <= 800 && quads <= 56) {
 #define BASD_OE(NV, MAXT) \
@@ -1262,9 +1269,12 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
     // square problems with a device-side active size (k x k principal-angle SVDs): those with
     // k <= 200 run register/shared-memory resident, the rest on the cluster kernel below
     constexpr int SMALL = 200;
-    if (int e = launch_oddeven<8, 7, 800>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
-                                          sweeps_out, st, 0, SMALL, rot_out))
-      return e;
+    int e = no_oe8 ? -100 : launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
+                                             sweeps_out, st, 0, SMALL, rot_out);
+    if (e == -100)
+      e = launch_oddeven<8, 7, 800>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out,
+                                    st, 0, SMALL, rot_out);
+    if (e) return e;
     lo = SMALL + 1;
   }
   // register-resident rows spread over a cluster (16 lanes per pair, 48 pairs per CTA)

@@ -1,0 +1,372 @@
+// One-sided Jacobi, register resident, EIGHT rows per 16-lane group.
+//
+// ncu on jacobi_rows_oddeven_kernel (two rows per 8-lane group) showed the odd steps of the
+// odd-even transposition ordering bound by shared-memory wavefronts: every group parks a row,
+// fetches its neighbour's, writes it back and reloads its own -- 4 row moves per row pair, 2,800
+// wavefronts per odd step at N = 196, while the FMA pipe idles (fast rotations changed nothing).
+// Here a group of 16 lanes owns 8 consecutive positions of the line: an even step rotates the
+// four resident pairs (0,1)(2,3)(4,5)(6,7), an odd step rotates (1,2)(3,4)(5,6) locally and only
+// (7, right neighbour's 0) crosses through shared memory, so the traffic per row drops 4x and the
+// three local pairs are computed between the two barriers of the exchange.  Four independent
+// pairs per thread also give the dot -> shuffle -> angle -> rotate chain instruction-level
+// parallelism that two-row groups lack.
+//
+// Rows are kept as  row = scale * stored  (scaled rotations: two FMAs per element pair), squared
+// norms are carried analytically with the determinant form for the shrinking row.
+// Serves the same contract as basd_jacobi_rows (reference: torch.linalg.svd / svdvals /
+// matrix_norm(ord="nuc"), layer_selector.py:92,99 and relational.py:48).
+#include "common.cuh"
+
+namespace basd {
+namespace oe8 {
+
+constexpr int R = 8;      // rows per group
+constexpr int G = 16;     // lanes per group
+
+struct RowState { float n, d; };   // squared norm of the actual row, scale (actual = d * stored)
+
+template <int NF>
+__device__ __forceinline__ void fold(float (&r)[NF], RowState& s) {
+#pragma unroll
+  for (int e = 0; e < NF; ++e) r[e] *= s.d;
+  s.d = 1.f;
+}
+
+template <int NF>
+__device__ __forceinline__ float dot_local(const float (&x)[NF], const float (&y)[NF]) {
+  float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+  for (int e = 0; e + 1 < NF; e += 2) {
+    g0 = fmaf(x[e], y[e], g0);
+    g1 = fmaf(x[e + 1], y[e + 1], g1);
+  }
+  if (NF & 1) g0 = fmaf(x[NF - 1], y[NF - 1], g0);
+  return g0 + g1;
+}
+
+// Rotation angle for the pair with (stored) dot product ga; updates norms / scales for the
+// rows AFTER they trade places; returns the two stored-row multipliers.
+__device__ __forceinline__ void angle(float ga, RowState& sx, RowState& sy, bool valid, float tol2,
+                                      float zero_thr, float& worst, int& nrot, float& t1,
+                                      float& t2) {
+  t1 = 0.f;
+  t2 = 0.f;
+  if (!valid) return;
+  ga *= sx.d * sy.d;
+  const float nx = sx.n, ny = sy.n;
+  const bool rot = (ga * ga > tol2 * nx * ny) && nx > zero_thr && ny > zero_thr;
+  float c = 1.f;
+  if (rot) {
+    ++nrot;
+    worst = fmaxf(worst, __fdividef(ga * ga, nx * ny));
+    const float d = ny - nx;
+    const float h = fmaf(d, d, 4.f * ga * ga);
+    const float root = h * rsqrtf(h);
+    float t = __fdividef(2.f * fabsf(ga), fabsf(d) + root);
+    t = ((d < 0.f) != (ga < 0.f)) ? -t : t;
+    const float w2 = fmaf(t, t, 1.f);
+    c = rsqrtf(w2);
+    c = c * fmaf(-0.5f * w2, c * c, 1.5f);
+    t1 = t * __fdividef(sx.d, sy.d);
+    t2 = t * __fdividef(sy.d, sx.d);
+    // larger row grows by |t g|; the smaller one is det / larger (no cancellation, jacobi.cu)
+    const float tg = t * ga;
+    const float big = (d >= 0.f) ? ny + tg : nx - tg;
+    const float r = __fdividef(1.f, big);
+    const float small = fmaxf(fmaf(nx, ny * r, -(ga * r) * ga), 0.f);
+    sx.n = (d >= 0.f) ? big : small;       // x will hold y'
+    sy.n = (d >= 0.f) ? small : big;       // y will hold x'
+  } else {
+    sx.n = ny;
+    sy.n = nx;
+  }
+  const float ndx = c * sy.d;
+  sy.d = c * sx.d;
+  sx.d = ndx;
+}
+
+// stored x <- stored y + t1 stored x ; stored y <- stored x - t2 stored y  (rows trade places)
+template <int NF>
+__device__ __forceinline__ void apply(float (&x)[NF], float (&y)[NF], bool valid, float t1, float t2) {
+  if (!valid) return;
+#pragma unroll
+  for (int e = 0; e < NF; ++e) {
+    const float a = x[e], b = y[e];
+    x[e] = fmaf(t1, a, b);
+    y[e] = fmaf(-t2, b, a);
+  }
+}
+
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// In-place pair in which the x row lives in shared memory (positions 0 of a group):
+//   first pass: partial dot product, second pass (after the angle): rotate and trade places.
+template <int NF>
+__device__ __forceinline__ float dot_smem(const float* __restrict__ xs_row, const float (&y)[NF]) {
+  float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+  for (int j = 0; j + 1 < NF; j += 2) {
+    g0 = fmaf(xs_row[G * j], y[j], g0);
+    g1 = fmaf(xs_row[G * (j + 1)], y[j + 1], g1);
+  }
+  if (NF & 1) g0 = fmaf(xs_row[G * (NF - 1)], y[NF - 1], g0);
+  return g0 + g1;
+}
+
+__device__ __forceinline__ float sel4(const float (&v)[4], int k) {
+  return k == 0 ? v[0] : (k == 1 ? v[1] : (k == 2 ? v[2] : v[3]));
+}
+
+// Row state (squared norm, scale) is DISTRIBUTED: lane p (1..7) of a group holds the state of
+// position p, position 0's state lives in shared memory next to its row.  The four angles of a
+// step are computed in ONE pass, each by the lane that owns the pair's left position (instead of
+// four redundant evaluations on all 16 lanes); partner states travel by shuffles (width 16) and
+// the two stored-row multipliers of every pair are broadcast back.
+template <int NF>    // floats per lane per row: columns lane + 16 j, j < NF
+__global__ void __launch_bounds__(448, 1)
+jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                       const int* __restrict__ dims, float tol, int max_sweeps,
+                       int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
+                       int* __restrict__ rot_out) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red_scratch[32];
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  if (dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;
+  const int gid = tid / G, gl = tid % G;
+  float* Gg = Gbase + (long)prob * stride;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
+  const int groups = (nn + R - 1) / R;
+  const int cnt = max(0, min(R, nn - gid * R));          // positions of this group that exist
+  constexpr int PITCH = NF * G;                          // floats per shared-memory row
+  const int nslots = blockDim.x / G + 1;
+  float2* xs = reinterpret_cast<float2*>(smem + (size_t)nslots * PITCH);   // state of every position 0
+  const int slot = min(gid, nslots - 1);
+  const int right = min(gid + 1, nslots - 1);
+  float* my_row = smem + (size_t)slot * PITCH + gl;      // position 0 of this group lives here
+  float* right_row = smem + (size_t)right * PITCH + gl;  // position 0 of the right neighbour
+
+  float r[R - 1][NF];                                    // r[i] = position i + 1
+  float sn = 0.f, sd = 1.f;                              // state of position gl (lanes 1..7)
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    const int c = gl + G * j;
+    my_row[G * j] = (cnt > 0 && c < mm) ? Gg[(long)(gid * R) * ld + c] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < R - 1; ++i) {
+    const int row = gid * R + i + 1;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const int c = gl + G * j;
+      r[i][j] = (i + 1 < cnt && c < mm) ? Gg[(long)row * ld + c] : 0.f;
+    }
+  }
+  const bool cross_ok = (cnt == R) && (gid + 1 < groups);   // right neighbour always owns a position 0
+  const float tol2 = tol * tol;
+  int nrot = 0;
+  int sweep = 0;
+  for (; sweep < max_sweeps && nn >= 2; ++sweep) {
+    // fold the scales into the rows, refresh the carried norms
+    float nrm[R];
+    {
+      const float d0 = sweep ? xs[slot].y : 1.f;
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const float v = my_row[G * j] * d0;
+        my_row[G * j] = v;
+        a = fmaf(v, v, a);
+      }
+      nrm[0] = a;
+    }
+#pragma unroll
+    for (int i = 0; i < R - 1; ++i) {
+      const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < NF; ++e) {
+        r[i][e] *= di;
+        a = fmaf(r[i][e], r[i][e], a);
+      }
+      nrm[i + 1] = a;
+    }
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) nrm[i] += __shfl_xor_sync(0xffffffffu, nrm[i], o);
+    }
+    sd = 1.f;
+    sn = 0.f;
+    float mxl = 0.f;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      mxl = fmaxf(mxl, nrm[i]);
+      if (gl == i) sn = nrm[i];
+    }
+    if (gl == 0) xs[slot] = make_float2(nrm[0], 1.f);
+    const float mx = block_max(mxl, red_scratch);        // (also orders the shared-memory writes above)
+    const float zero_thr = 1e-14f * mx;
+    float worst = 0.f;
+    for (int step = 0; step < nn; ++step) {
+      float ga[4], T1[4], T2[4];
+      const int odd = step & 1;
+      if (!odd) {
+        if ((step & 15) == 0 && step) {                  // fold the scales (they shrink by c per rotation)
+          const float d0 = xs[slot].y;
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < NF; ++j) my_row[G * j] *= d0;
+          if (gl == 0) xs[slot].y = 1.f;
+#pragma unroll
+          for (int i = 0; i < R - 1; ++i) {
+            const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
+#pragma unroll
+            for (int e = 0; e < NF; ++e) r[i][e] *= di;
+          }
+          sd = 1.f;
+          __syncwarp();
+        }
+        ga[0] = dot_smem<NF>(my_row, r[0]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) ga[k] = dot_local<NF>(r[2 * k - 1], r[2 * k]);
+      } else {
+        ga[3] = dot_smem<NF>(right_row, r[R - 2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ga[k] = dot_local<NF>(r[2 * k], r[2 * k + 1]);
+      }
+#pragma unroll
+      for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ga[k] += __shfl_xor_sync(0xffffffffu, ga[k], o);
+      }
+      // ---- one angle pass: lane p (p < 8, p parity = step parity) owns the pair (p, p + 1)
+      const bool owner = gl < R && (gl & 1) == odd;
+      const bool from_smem_x = !odd && gl == 0;          // x = position 0 (even steps)
+      const bool from_smem_y = odd && gl == R - 1;       // y = right neighbour's position 0 (odd steps)
+      const float pn = __shfl_down_sync(0xffffffffu, sn, 1, G);
+      const float pd = __shfl_down_sync(0xffffffffu, sd, 1, G);
+      RowState sx{sn, sd}, sy{pn, pd};
+      if (from_smem_x) { const float2 v = xs[slot]; sx.n = v.x; sx.d = v.y; }
+      if (from_smem_y) { const float2 v = xs[right]; sy.n = v.x; sy.d = v.y; }
+      const bool valid = owner && (from_smem_y ? cross_ok : (gl + 1 < cnt));
+      float t1, t2;
+      angle(sel4(ga, gl >> 1), sx, sy, valid, tol2, zero_thr, worst, nrot, t1, t2);
+      // new states: x's position keeps sx, the partner position receives sy
+      if (from_smem_x) xs[slot] = make_float2(sx.n, sx.d);
+      else if (owner) { sn = sx.n; sd = sx.d; }
+      if (from_smem_y && valid) xs[right] = make_float2(sy.n, sy.d);
+      {
+        const float rn = __shfl_up_sync(0xffffffffu, sy.n, 1, G);
+        const float rd = __shfl_up_sync(0xffffffffu, sy.d, 1, G);
+        const bool receiver = gl >= 1 && gl < R && ((gl - 1) & 1) == odd;
+        if (receiver) { sn = rn; sd = rd; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        T1[k] = __shfl_sync(0xffffffffu, t1, 2 * k + odd, G);
+        T2[k] = __shfl_sync(0xffffffffu, t2, 2 * k + odd, G);
+      }
+      // ---- apply the four rotations (invalid pairs carry t1 = t2 = 0 and are skipped)
+      if (!odd) {
+        if (1 < cnt) {
+#pragma unroll
+          for (int j = 0; j < NF; ++j) {
+            const float a = my_row[G * j], b = r[0][j];
+            my_row[G * j] = fmaf(T1[0], a, b);
+            r[0][j] = fmaf(-T2[0], b, a);
+          }
+        }
+#pragma unroll
+        for (int k = 1; k < 4; ++k) apply<NF>(r[2 * k - 1], r[2 * k], 2 * k + 1 < cnt, T1[k], T2[k]);
+      } else {
+        if (cross_ok) {
+#pragma unroll
+          for (int j = 0; j < NF; ++j) {
+            const float a = r[R - 2][j], b = right_row[G * j];
+            r[R - 2][j] = fmaf(T1[3], a, b);
+            right_row[G * j] = fmaf(-T2[3], b, a);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) apply<NF>(r[2 * k], r[2 * k + 1], 2 * k + 2 < cnt, T1[k], T2[k]);
+      }
+      __syncthreads();
+    }
+    worst = block_max(worst, red_scratch);
+    if (worst < tol) { ++sweep; break; }
+  }
+  {
+    const float d0 = (nn >= 2 && sweep) ? xs[slot].y : 1.f;
+    if (cnt > 0) {
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int c = gl + G * j;
+        if (c < mm) Gg[(long)(gid * R) * ld + c] = my_row[G * j] * d0;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < R - 1; ++i) {
+    const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
+    const int row = gid * R + i + 1;
+    if (i + 1 < cnt) {
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int c = gl + G * j;
+        if (c < mm) Gg[(long)row * ld + c] = r[i][j] * di;
+      }
+    }
+  }
+  if (sweeps_out && tid == 0) sweeps_out[prob] = sweep;
+  if (rot_out) {
+    const float tot = block_sum((float)nrot, red_scratch);
+    if (tid == 0) atomicAdd(rot_out + prob, (int)tot);
+  }
+}
+
+template <int NF>
+static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
+                  int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo, int dim_hi,
+                  int* rot_out) {
+  const int cap = (dims && dim_hi < n) ? dim_hi : n;
+  int threads = ((cap + R - 1) / R) * G;
+  threads = (threads + 31) / 32 * 32;
+  if (threads < 64) threads = 64;
+  const size_t nslots = threads / G + 1;
+  const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
+  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)dyn));
+  jacobi_rows_oe8_kernel<NF><<<batch, threads, dyn, st>>>(Gm, n, m, ld, stride, dims, tol, max_sweeps,
+                                                          sweeps_out, dim_lo, dim_hi, rot_out);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace oe8
+
+// Problems with at most 224 active rows and 224 active columns (the per-sample Procrustes SVDs
+// and the k x k principal-angle SVDs).  Returns -100 when the shape does not fit.
+int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                      float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                      int dim_hi, int* rot_out) {
+  const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
+  const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
+  if (cap_n > 224 || cap_m > 224) return -100;
+#define BASD_OE8(NF) \
+  return oe8::launch<NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+  if (cap_m <= 64) BASD_OE8(4);
+  if (cap_m <= 96) BASD_OE8(6);
+  if (cap_m <= 128) BASD_OE8(8);
+  if (cap_m <= 160) BASD_OE8(10);
+  if (cap_m <= 192) BASD_OE8(12);
+  if (cap_m <= 208) BASD_OE8(13);
+  BASD_OE8(14);
+#undef BASD_OE8
+}
+
+}  // namespace basd
