@@ -16,12 +16,12 @@
 // Serves the same contract as basd_jacobi_rows (reference: torch.linalg.svd / svdvals /
 // matrix_norm(ord="nuc"), layer_selector.py:92,99 and relational.py:48).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace basd {
 namespace oe8 {
 
 constexpr int R = 8;      // rows per group
-constexpr int G = 16;     // lanes per group
 
 struct RowState { float n, d; };   // squared norm of the actual row, scale (actual = d * stored)
 
@@ -45,44 +45,44 @@ __device__ __forceinline__ float dot_local(const float (&x)[NF], const float (&y
 }
 
 // Rotation angle for the pair with (stored) dot product ga; updates norms / scales for the
-// rows AFTER they trade places; returns the two stored-row multipliers.
+// rows AFTER they trade places; returns the two stored-row multipliers.  Branch free: every lane
+// evaluates the formulas, `valid` / `rot` only select the results.
 __device__ __forceinline__ void angle(float ga, RowState& sx, RowState& sy, bool valid, float tol2,
                                       float zero_thr, float& worst, int& nrot, float& t1,
                                       float& t2) {
-  t1 = 0.f;
-  t2 = 0.f;
-  if (!valid) return;
   ga *= sx.d * sy.d;
   const float nx = sx.n, ny = sy.n;
-  const bool rot = (ga * ga > tol2 * nx * ny) && nx > zero_thr && ny > zero_thr;
-  float c = 1.f;
-  if (rot) {
-    ++nrot;
-    worst = fmaxf(worst, __fdividef(ga * ga, nx * ny));
-    const float d = ny - nx;
-    const float h = fmaf(d, d, 4.f * ga * ga);
-    const float root = h * rsqrtf(h);
-    float t = __fdividef(2.f * fabsf(ga), fabsf(d) + root);
-    t = ((d < 0.f) != (ga < 0.f)) ? -t : t;
-    const float w2 = fmaf(t, t, 1.f);
-    c = rsqrtf(w2);
-    c = c * fmaf(-0.5f * w2, c * c, 1.5f);
-    t1 = t * __fdividef(sx.d, sy.d);
-    t2 = t * __fdividef(sy.d, sx.d);
-    // larger row grows by |t g|; the smaller one is det / larger (no cancellation, jacobi.cu)
-    const float tg = t * ga;
-    const float big = (d >= 0.f) ? ny + tg : nx - tg;
-    const float r = __fdividef(1.f, big);
-    const float small = fmaxf(fmaf(nx, ny * r, -(ga * r) * ga), 0.f);
-    sx.n = (d >= 0.f) ? big : small;       // x will hold y'
-    sy.n = (d >= 0.f) ? small : big;       // y will hold x'
-  } else {
-    sx.n = ny;
-    sy.n = nx;
-  }
-  const float ndx = c * sy.d;
-  sy.d = c * sx.d;
-  sx.d = ndx;
+  const float gg = ga * ga, nxy = nx * ny;
+  const bool rot = valid && (gg > tol2 * nxy) && nx > zero_thr && ny > zero_thr;
+  nrot += rot ? 1 : 0;
+  worst = fmaxf(worst, rot ? __fdividef(gg, nxy) : 0.f);
+  const float d = ny - nx;
+  const float h = fmaf(d, d, 4.f * gg);
+  const float root = h * rsqrtf(fmaxf(h, 1e-37f));
+  float t = __fdividef(2.f * fabsf(ga), fmaxf(fabsf(d) + root, 1e-37f));
+  t = ((d < 0.f) != (ga < 0.f)) ? -t : t;
+  t = rot ? t : 0.f;
+  const float w2 = fmaf(t, t, 1.f);
+  float c = rsqrtf(w2);
+  c = c * fmaf(-0.5f * w2, c * c, 1.5f);
+  const float dx = sx.d, dy = sy.d;
+  t1 = t * __fdividef(dx, dy);
+  t2 = t * __fdividef(dy, dx);
+  t1 = rot ? t1 : 0.f;
+  t2 = rot ? t2 : 0.f;
+  // larger row grows by |t g|; the smaller one is det / larger (no cancellation, jacobi.cu)
+  const float tg = t * ga;
+  const bool ybig = d >= 0.f;
+  const float big = ybig ? ny + tg : nx - tg;
+  const float r = __fdividef(1.f, fmaxf(big, 1e-37f));
+  const float small = fmaxf(fmaf(nx, ny * r, -(ga * r) * ga), 0.f);
+  // rows trade places when the pair is valid (rotated or not)
+  const float nxn = rot ? (ybig ? big : small) : ny;      // x will hold y'
+  const float nyn = rot ? (ybig ? small : big) : nx;      // y will hold x'
+  sx.n = valid ? nxn : nx;
+  sy.n = valid ? nyn : ny;
+  sx.d = valid ? c * dy : dx;
+  sy.d = valid ? c * dx : dy;
 }
 
 // stored x <- stored y + t1 stored x ; stored y <- stored x - t2 stored y  (rows trade places)
@@ -97,15 +97,9 @@ __device__ __forceinline__ void apply(float (&x)[NF], float (&y)[NF], bool valid
   }
 }
 
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // In-place pair in which the x row lives in shared memory (positions 0 of a group):
 //   first pass: partial dot product, second pass (after the angle): rotate and trade places.
-template <int NF>
+template <int G, int NF>
 __device__ __forceinline__ float dot_smem(const float* __restrict__ xs_row, const float (&y)[NF]) {
   float g0 = 0.f, g1 = 0.f;
 #pragma unroll
@@ -117,8 +111,65 @@ __device__ __forceinline__ float dot_smem(const float* __restrict__ xs_row, cons
   return g0 + g1;
 }
 
+// Sum four per-lane partials over the G lanes of a group with a transpose-reduce: the first
+// two stages halve the number of live values (2 + 1 shuffles), the remaining stages carry one.
+// Returns, on EVERY lane, the full sum of value (gl >> 1) & 3 -- exactly the pair a lane may own
+// in the angle pass (owner lane p handles pair p >> 1) -- fetched with one last shuffle.
+template <int G>
+__device__ __forceinline__ float reduce4_owner(const float (&v)[4], int gl) {
+  constexpr int H = G >> 1, Q = G >> 2;
+  // stage 1 (xor H): lanes with bit H clear keep values {0,1}, the others {2,3}
+  const bool up = (gl & H) != 0;
+  const float s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];      // what this lane gives away
+  const float k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];      // what it keeps
+  const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, H);
+  const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, H);
+  // stage 2 (xor Q): bit Q clear keeps the first of the two, set keeps the second
+  const bool up2 = (gl & Q) != 0;
+  float b = (up2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up2 ? a0 : a1, Q);
+#pragma unroll
+  for (int o = Q >> 1; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+  // lane gl now holds the sum of value 2*[bit H] + [bit Q]; owner of pair k reads it from lane k*Q
+  const int k = (gl >> 1) & 3;
+  return __shfl_sync(0xffffffffu, b, ((k >> 1) * H) + ((k & 1) * Q), G);
+}
+
 __device__ __forceinline__ float sel4(const float (&v)[4], int k) {
   return k == 0 ? v[0] : (k == 1 ? v[1] : (k == 2 ? v[2] : v[3]));
+}
+
+// One angle pass of a step with parity ODD: lane p (p < 8, parity of p = ODD) owns the pair
+// (p, p + 1); position 0 (even steps) and the right neighbour's position 0 (odd steps) keep
+// their state in shared memory.
+template <int G, int ODD>
+__device__ __forceinline__ void angle_pass(float g_own, float& sn, float& sd, float2* xs,
+                                           int slot, int right, int gl, int cnt, bool cross_ok,
+                                           float tol2, float zero_thr, float& worst, int& nrot,
+                                           float (&T1)[4], float (&T2)[4]) {
+  const bool owner = gl < R && (gl & 1) == ODD;
+  const bool from_smem_x = !ODD && gl == 0;            // x = position 0 (even steps)
+  const bool from_smem_y = ODD && gl == R - 1;         // y = right neighbour's position 0 (odd steps)
+  const float pn = __shfl_down_sync(0xffffffffu, sn, 1, G);
+  const float pd = __shfl_down_sync(0xffffffffu, sd, 1, G);
+  RowState sx{sn, sd}, sy{pn, pd};
+  if (from_smem_x) { const float2 v = xs[slot]; sx.n = v.x; sx.d = v.y; }
+  if (from_smem_y) { const float2 v = xs[right]; sy.n = v.x; sy.d = v.y; }
+  const bool valid = owner && (from_smem_y ? cross_ok : (gl + 1 < cnt));
+  float t1, t2;
+  angle(g_own, sx, sy, valid, tol2, zero_thr, worst, nrot, t1, t2);
+  // new states: x's position keeps sx, the partner position receives sy
+  if (from_smem_x) xs[slot] = make_float2(sx.n, sx.d);
+  else if (owner) { sn = sx.n; sd = sx.d; }
+  if (from_smem_y && valid) xs[right] = make_float2(sy.n, sy.d);
+  const float rn = __shfl_up_sync(0xffffffffu, sy.n, 1, G);
+  const float rd = __shfl_up_sync(0xffffffffu, sy.d, 1, G);
+  const bool receiver = gl >= 1 && gl < R && ((gl - 1) & 1) == ODD;
+  if (receiver) { sn = rn; sd = rd; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    T1[k] = __shfl_sync(0xffffffffu, t1, 2 * k + ODD, G);
+    T2[k] = __shfl_sync(0xffffffffu, t2, 2 * k + ODD, G);
+  }
 }
 
 // Row state (squared norm, scale) is DISTRIBUTED: lane p (1..7) of a group holds the state of
@@ -126,8 +177,8 @@ __device__ __forceinline__ float sel4(const float (&v)[4], int k) {
 // step are computed in ONE pass, each by the lane that owns the pair's left position (instead of
 // four redundant evaluations on all 16 lanes); partner states travel by shuffles (width 16) and
 // the two stored-row multipliers of every pair are broadcast back.
-template <int NF>    // floats per lane per row: columns lane + 16 j, j < NF
-__global__ void __launch_bounds__(448, 1)
+template <int G, int NF>    // G lanes per group; NF floats per lane per row: columns lane + G j, j < NF
+__global__ void __launch_bounds__(G == 16 ? 448 : 896, 1)
 jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                        const int* __restrict__ dims, float tol, int max_sweeps,
                        int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
@@ -212,78 +263,46 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
     const float mx = block_max(mxl, red_scratch);        // (also orders the shared-memory writes above)
     const float zero_thr = 1e-14f * mx;
     float worst = 0.f;
-    for (int step = 0; step < nn; ++step) {
+#pragma unroll 2
+    for (int step = 0; step < nn; step += 2) {
       float ga[4], T1[4], T2[4];
-      const int odd = step & 1;
-      if (!odd) {
-        if ((step & 15) == 0 && step) {                  // fold the scales (they shrink by c per rotation)
-          const float d0 = xs[slot].y;
-          __syncwarp();
+      // ---------------- even step: (0,1) with position 0 in shared memory, (2,3) (4,5) (6,7)
+      if ((step & 15) == 0 && step) {                  // fold the scales (they shrink by c per rotation)
+        const float d0 = xs[slot].y;
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < NF; ++j) my_row[G * j] *= d0;
-          if (gl == 0) xs[slot].y = 1.f;
+        for (int j = 0; j < NF; ++j) my_row[G * j] *= d0;
+        if (gl == 0) xs[slot].y = 1.f;
 #pragma unroll
-          for (int i = 0; i < R - 1; ++i) {
-            const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
+        for (int i = 0; i < R - 1; ++i) {
+          const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
 #pragma unroll
-            for (int e = 0; e < NF; ++e) r[i][e] *= di;
-          }
-          sd = 1.f;
-          __syncwarp();
+          for (int e = 0; e < NF; ++e) r[i][e] *= di;
         }
-        ga[0] = dot_smem<NF>(my_row, r[0]);
+        sd = 1.f;
+        __syncwarp();
+      }
+      ga[0] = dot_smem<G, NF>(my_row, r[0]);
 #pragma unroll
-        for (int k = 1; k < 4; ++k) ga[k] = dot_local<NF>(r[2 * k - 1], r[2 * k]);
-      } else {
-        ga[3] = dot_smem<NF>(right_row, r[R - 2]);
+      for (int k = 1; k < 4; ++k) ga[k] = dot_local<NF>(r[2 * k - 1], r[2 * k]);
+      angle_pass<G, 0>(reduce4_owner<G>(ga, gl), sn, sd, xs, slot, right, gl, cnt, cross_ok, tol2, zero_thr, worst, nrot, T1, T2);
+      if (1 < cnt) {
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+          const float a = my_row[G * j], b = r[0][j];
+          my_row[G * j] = fmaf(T1[0], a, b);
+          r[0][j] = fmaf(-T2[0], b, a);
+        }
+      }
+#pragma unroll
+      for (int k = 1; k < 4; ++k) apply<NF>(r[2 * k - 1], r[2 * k], 2 * k + 1 < cnt, T1[k], T2[k]);
+      __syncthreads();
+      // ---------------- odd step: (1,2) (3,4) (5,6), (7, right neighbour's 0) through shared memory
+      if (step + 1 < nn) {
+        ga[3] = dot_smem<G, NF>(right_row, r[R - 2]);
 #pragma unroll
         for (int k = 0; k < 3; ++k) ga[k] = dot_local<NF>(r[2 * k], r[2 * k + 1]);
-      }
-#pragma unroll
-      for (int o = G >> 1; o > 0; o >>= 1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ga[k] += __shfl_xor_sync(0xffffffffu, ga[k], o);
-      }
-      // ---- one angle pass: lane p (p < 8, p parity = step parity) owns the pair (p, p + 1)
-      const bool owner = gl < R && (gl & 1) == odd;
-      const bool from_smem_x = !odd && gl == 0;          // x = position 0 (even steps)
-      const bool from_smem_y = odd && gl == R - 1;       // y = right neighbour's position 0 (odd steps)
-      const float pn = __shfl_down_sync(0xffffffffu, sn, 1, G);
-      const float pd = __shfl_down_sync(0xffffffffu, sd, 1, G);
-      RowState sx{sn, sd}, sy{pn, pd};
-      if (from_smem_x) { const float2 v = xs[slot]; sx.n = v.x; sx.d = v.y; }
-      if (from_smem_y) { const float2 v = xs[right]; sy.n = v.x; sy.d = v.y; }
-      const bool valid = owner && (from_smem_y ? cross_ok : (gl + 1 < cnt));
-      float t1, t2;
-      angle(sel4(ga, gl >> 1), sx, sy, valid, tol2, zero_thr, worst, nrot, t1, t2);
-      // new states: x's position keeps sx, the partner position receives sy
-      if (from_smem_x) xs[slot] = make_float2(sx.n, sx.d);
-      else if (owner) { sn = sx.n; sd = sx.d; }
-      if (from_smem_y && valid) xs[right] = make_float2(sy.n, sy.d);
-      {
-        const float rn = __shfl_up_sync(0xffffffffu, sy.n, 1, G);
-        const float rd = __shfl_up_sync(0xffffffffu, sy.d, 1, G);
-        const bool receiver = gl >= 1 && gl < R && ((gl - 1) & 1) == odd;
-        if (receiver) { sn = rn; sd = rd; }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        T1[k] = __shfl_sync(0xffffffffu, t1, 2 * k + odd, G);
-        T2[k] = __shfl_sync(0xffffffffu, t2, 2 * k + odd, G);
-      }
-      // ---- apply the four rotations (invalid pairs carry t1 = t2 = 0 and are skipped)
-      if (!odd) {
-        if (1 < cnt) {
-#pragma unroll
-          for (int j = 0; j < NF; ++j) {
-            const float a = my_row[G * j], b = r[0][j];
-            my_row[G * j] = fmaf(T1[0], a, b);
-            r[0][j] = fmaf(-T2[0], b, a);
-          }
-        }
-#pragma unroll
-        for (int k = 1; k < 4; ++k) apply<NF>(r[2 * k - 1], r[2 * k], 2 * k + 1 < cnt, T1[k], T2[k]);
-      } else {
+        angle_pass<G, 1>(reduce4_owner<G>(ga, gl), sn, sd, xs, slot, right, gl, cnt, cross_ok, tol2, zero_thr, worst, nrot, T1, T2);
         if (cross_ok) {
 #pragma unroll
           for (int j = 0; j < NF; ++j) {
@@ -329,7 +348,7 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
   }
 }
 
-template <int NF>
+template <int G, int NF>
 static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
                   int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo, int dim_hi,
                   int* rot_out) {
@@ -339,9 +358,9 @@ static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const
   if (threads < 64) threads = 64;
   const size_t nslots = threads / G + 1;
   const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
-  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_kernel<G, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dyn));
-  jacobi_rows_oe8_kernel<NF><<<batch, threads, dyn, st>>>(Gm, n, m, ld, stride, dims, tol, max_sweeps,
+  jacobi_rows_oe8_kernel<G, NF><<<batch, threads, dyn, st>>>(Gm, n, m, ld, stride, dims, tol, max_sweeps,
                                                           sweeps_out, dim_lo, dim_hi, rot_out);
   BASD_LAUNCH_CHECK();
   return 0;
@@ -357,8 +376,18 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
   const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
   const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
   if (cap_n > 224 || cap_m > 224) return -100;
+  // 32 lanes per group: twice the warps per SM for the same work, 72 registers
+  static const bool wide = getenv("BASD_JACOBI_OE8_G32") != nullptr;   // measured slower (25.1 vs 19.7 ms at C2): opt-in only
 #define BASD_OE8(NF) \
-  return oe8::launch<NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+  return oe8::launch<16, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+#define BASD_OE8W(NF) \
+  return oe8::launch<32, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+  if (wide && cap_n > 64) {
+    if (cap_m <= 128) BASD_OE8W(4);
+    if (cap_m <= 160) BASD_OE8W(5);
+    if (cap_m <= 192) BASD_OE8W(6);
+    BASD_OE8W(7);
+  }
   if (cap_m <= 64) BASD_OE8(4);
   if (cap_m <= 96) BASD_OE8(6);
   if (cap_m <= 128) BASD_OE8(8);
@@ -366,6 +395,7 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
   if (cap_m <= 192) BASD_OE8(12);
   if (cap_m <= 208) BASD_OE8(13);
   BASD_OE8(14);
+#undef BASD_OE8W
 #undef BASD_OE8
 }
 

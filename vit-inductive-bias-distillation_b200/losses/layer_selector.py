@@ -116,6 +116,7 @@ class GrassmannianLayerSelector(nn.Module):
         self.process_group = None
         self.sync_stats = True
         self.last_state = None
+        self.last_step = None
 
     @property
     def temperatures(self) -> torch.Tensor:
@@ -140,6 +141,7 @@ class GrassmannianLayerSelector(nn.Module):
         weights = MixingWeights.apply(self.log_temperatures, step, *students)
         self.subspace_ranks._stage(sorted(all_teacher_tokens.keys()), step.selector.ranks)
         self.last_state = step.selector
+        self.last_step = step
         return weights, step
 
     def forward(self, student_tokens_per_layer, all_teacher_tokens, all_teacher_attns,
