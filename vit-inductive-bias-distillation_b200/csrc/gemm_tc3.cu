@@ -106,35 +106,41 @@ __device__ __forceinline__ uint32_t sw_off(int row, int k) {
                                ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
 }
 
+// The producers keep TWO register sets of raw tiles: the global loads of slab kb+1 are in flight
+// while slab kb is split and written to shared memory (a slab is only ~43 KB, so without this the
+// K loop runs at one global-memory latency per slab).
+//
 // Operand whose contraction index is contiguous in memory (row-major R x K with pitch ld):
 // one float4 = 4 consecutive k of one row; a quarter warp covers one 128-byte row -> conflict-free
-// 128-bit stores.
-__device__ __forceinline__ void load_kcontig(const float* __restrict__ g, int ld, int r0, int R,
-                                             int row_limit, int k0, int K, uint8_t* hi,
-                                             uint8_t* lo, int ptid) {
+// 128-bit stores.  Item f of a thread: f = ptid + u * PRODUCERS, row = f / 8, chunk = f % 8.
+template <int CNT>
+__device__ __forceinline__ void issue_kcontig(float4 (&v)[CNT], const float* __restrict__ g, int ld,
+                                              int r0, int R, int row_limit, int k0, int K, int ptid) {
   const int items = R * 8;
-  for (int base = ptid; base < items; base += PRODUCERS * 4) {
-    float4 v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int f = base + u * PRODUCERS;
+  for (int u = 0; u < CNT; ++u) {
+    const int f = ptid + u * PRODUCERS;
+    const int row = f >> 3, ch = f & 7;
+    const int gr = r0 + row, gk = k0 + ch * 4;
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f < items && gr < row_limit && gk < K)
+      v[u] = __ldg(reinterpret_cast<const float4*>(g + static_cast<long>(gr) * ld + gk));
+  }
+}
+template <int CNT>
+__device__ __forceinline__ void store_kcontig(const float4 (&v)[CNT], int R, uint8_t* hi, uint8_t* lo,
+                                              int ptid) {
+  const int items = R * 8;
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    const int f = ptid + u * PRODUCERS;
+    if (f < items) {
       const int row = f >> 3, ch = f & 7;
-      const int gr = r0 + row, gk = k0 + ch * 4;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (f < items && gr < row_limit && gk < K)
-        v[u] = __ldg(reinterpret_cast<const float4*>(g + static_cast<long>(gr) * ld + gk));
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int f = base + u * PRODUCERS;
-      if (f < items) {
-        const int row = f >> 3, ch = f & 7;
-        float4 h, l;
-        split4(v[u], h, l);
-        const uint32_t off = sw_off(row, ch * 4);
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
-      }
+      float4 h, l;
+      split4(v[u], h, l);
+      const uint32_t off = sw_off(row, ch * 4);
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
     }
   }
 }
@@ -142,41 +148,49 @@ __device__ __forceinline__ void load_kcontig(const float* __restrict__ g, int ld
 // Operand whose contraction index is the slow dimension in memory (row-major K x R with pitch
 // ld): one float4 = 4 consecutive rows of the slab at one k; transposed by scalar stores.  A warp
 // covers 16 k x 2 row-quads: the 32 scalar stores of each of the 4 components hit 32 banks.
-__device__ __forceinline__ void load_mncontig(const float* __restrict__ g, int ld, int r0, int R,
-                                              int row_limit, int k0, int K, uint8_t* hi,
-                                              uint8_t* lo, int ptid) {
+// Block blk of a warp: blk = warp + u * PRODUCER_WARPS over (row octets) x (two halves of the slab).
+template <int CNT>
+__device__ __forceinline__ void issue_mncontig(float4 (&v)[CNT], const float* __restrict__ g, int ld,
+                                               int r0, int R, int row_limit, int k0, int K, int ptid) {
   const int lane = ptid & 31, warp = ptid >> 5;
   const int kk = lane & 15, ql = lane >> 4;
-  const int blocks = (R >> 3) * 2;                       // (row octets) x (two halves of the slab)
-  for (int base = warp; base < blocks; base += PRODUCER_WARPS * 4) {
-    float4 v[4];
+  const int blocks = (R >> 3) * 2;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int blk = base + u * PRODUCER_WARPS;
+  for (int u = 0; u < CNT; ++u) {
+    const int blk = warp + u * PRODUCER_WARPS;
+    const int k = (blk & 1) * 16 + kk, row = (blk >> 1) * 8 + ql * 4;
+    const int gk = k0 + k, gr = r0 + row;
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (blk < blocks && gk < K && gr < row_limit)
+      v[u] = __ldg(reinterpret_cast<const float4*>(g + static_cast<long>(gk) * ld + gr));
+  }
+}
+template <int CNT>
+__device__ __forceinline__ void store_mncontig(const float4 (&v)[CNT], int R, uint8_t* hi, uint8_t* lo,
+                                               int ptid) {
+  const int lane = ptid & 31, warp = ptid >> 5;
+  const int kk = lane & 15, ql = lane >> 4;
+  const int blocks = (R >> 3) * 2;
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    const int blk = warp + u * PRODUCER_WARPS;
+    if (blk < blocks) {
       const int k = (blk & 1) * 16 + kk, row = (blk >> 1) * 8 + ql * 4;
-      const int gk = k0 + k, gr = r0 + row;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (blk < blocks && gk < K && gr < row_limit)
-        v[u] = __ldg(reinterpret_cast<const float4*>(g + static_cast<long>(gk) * ld + gr));
-    }
+      float4 h, l;
+      split4(v[u], h, l);
+      const float hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int blk = base + u * PRODUCER_WARPS;
-      if (blk < blocks) {
-        const int k = (blk & 1) * 16 + kk, row = (blk >> 1) * 8 + ql * 4;
-        float4 h, l;
-        split4(v[u], h, l);
-        const float hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t off = sw_off(row + i, k);
-          *reinterpret_cast<float*>(hi + off) = hv[i];
-          *reinterpret_cast<float*>(lo + off) = lv[i];
-        }
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = sw_off(row + i, k);
+        *reinterpret_cast<float*>(hi + off) = hv[i];
+        *reinterpret_cast<float*>(lo + off) = lv[i];
       }
     }
   }
 }
+
+constexpr int A_ITEMS = TM * 8 / PRODUCERS;             // 4 float4 per producer thread
+constexpr int B_ITEMS = 256 * 8 / PRODUCERS;            // 8 (BN <= 256)
 
 struct Params {
   const float* A; const float* B; float* C;
@@ -228,7 +242,15 @@ gemm_tc3_kernel(const Params p) {
   if (warp < PRODUCER_WARPS) {
     // ===== producers =====
     const int ptid = threadIdx.x;
-    for (int kb = 0; kb < num_kb; ++kb) {
+    float4 va[2][A_ITEMS], vb[2][B_ITEMS];
+    auto issue = [&](int set, int kb) {
+      const int k0 = kb * KS;
+      if (p.ta) issue_mncontig<A_ITEMS>(va[set], A, p.lda, m0, TM, p.M, k0, p.K, ptid);
+      else      issue_kcontig<A_ITEMS>(va[set], A, p.lda, m0, TM, p.M, k0, p.K, ptid);
+      if (p.tb) issue_kcontig<B_ITEMS>(vb[set], B, p.ldb, n0, p.BN, p.N, k0, p.K, ptid);
+      else      issue_mncontig<B_ITEMS>(vb[set], B, p.ldb, n0, p.BN, p.N, k0, p.K, ptid);
+    };
+    auto publish = [&](int set, int kb) {
       const int s = kb % p.stages;
       const uint32_t ph = (kb / p.stages) & 1;
       mbar_wait(&empty_bar[s], ph ^ 1);
@@ -236,14 +258,20 @@ gemm_tc3_kernel(const Params p) {
       uint8_t* a_lo = a_hi + A_BYTES;
       uint8_t* b_hi = a_lo + A_BYTES;
       uint8_t* b_lo = b_hi + b_bytes;
-      const int k0 = kb * KS;
-      if (p.ta) load_mncontig(A, p.lda, m0, TM, p.M, k0, p.K, a_hi, a_lo, ptid);
-      else      load_kcontig(A, p.lda, m0, TM, p.M, k0, p.K, a_hi, a_lo, ptid);
-      if (p.tb) load_kcontig(B, p.ldb, n0, p.BN, p.N, k0, p.K, b_hi, b_lo, ptid);
-      else      load_mncontig(B, p.ldb, n0, p.BN, p.N, k0, p.K, b_hi, b_lo, ptid);
+      if (p.ta) store_mncontig<A_ITEMS>(va[set], TM, a_hi, a_lo, ptid);
+      else      store_kcontig<A_ITEMS>(va[set], TM, a_hi, a_lo, ptid);
+      if (p.tb) store_kcontig<B_ITEMS>(vb[set], p.BN, b_hi, b_lo, ptid);
+      else      store_mncontig<B_ITEMS>(vb[set], p.BN, b_hi, b_lo, ptid);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> UMMA reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+    };
+    if (num_kb > 0) issue(0, 0);
+    for (int kb = 0; kb < num_kb; kb += 2) {
+      if (kb + 1 < num_kb) issue(1, kb + 1);
+      publish(0, kb);
+      if (kb + 2 < num_kb) issue(0, kb + 2);
+      if (kb + 1 < num_kb) publish(1, kb + 1);
     }
   } else if (lane == 0) {
     // ===== MMA issuer (one thread) =====

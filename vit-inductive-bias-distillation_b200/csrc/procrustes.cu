@@ -14,6 +14,83 @@
 namespace basd {
 
 // out[n,:] = sqrt(w_n) (x[n,:] - sum_m w_m x[m,:])           (relational.py:36-43)
+// Columns are independent, so a sample is split over gridDim.y column slices of CW columns;
+// inside a block every thread owns VEC adjacent columns (one 128-bit load) and the row groups
+// stride over the tokens: pass 1 accumulates the weighted column means, pass 2 re-reads the
+// (L2-resident) rows and writes fp32.
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) { load8(p, v); }
+};
+
+template <typename T, int CW>
+__global__ void __launch_bounds__(256)
+weighted_center_vec_kernel(const T* __restrict__ X, long strideX, const float* __restrict__ W,
+                           long strideW, int N, int D, float* __restrict__ out, long strideO) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int CT = CW / VEC;                 // threads across the columns of the slice
+  constexpr int RG = 256 / CT;                 // row groups
+  extern __shared__ float sm[];
+  float* w = sm;                               // N
+  float* rw = sm + N;                          // N
+  float* part = rw + N;                        // RG x CW partial means
+  const int s = blockIdx.x;
+  const int ct = threadIdx.x % CT, rg = threadIdx.x / CT;
+  const int c0 = blockIdx.y * CW + ct * VEC;
+  const T* x = X + (long)s * strideX;
+  float* o = out + (long)s * strideO;
+  for (int n = threadIdx.x; n < N; n += 256) {
+    const float v = W[(long)s * strideW + n];
+    w[n] = v;
+    rw[n] = sqrtf(v);
+  }
+  __syncthreads();
+  const bool live = c0 < D && rg < RG;
+  float mu[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) mu[i] = 0.f;
+  if (live) {
+    for (int n = rg; n < N; n += RG) {
+      float v[VEC];
+      Vec16<T>::load(x + (long)n * D + c0, v);
+      const float wn = w[n];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) mu[i] = fmaf(wn, v[i], mu[i]);
+    }
+  }
+  if (rg < RG) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) part[rg * CW + ct * VEC + i] = mu[i];
+  }
+  __syncthreads();
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float t = 0.f;
+      for (int g = 0; g < RG; ++g) t += part[g * CW + ct * VEC + i];   // same order in every row group
+      mu[i] = t;
+    }
+    for (int n = rg; n < N; n += RG) {
+      float v[VEC];
+      Vec16<T>::load(x + (long)n * D + c0, v);
+      const float r = rw[n];
+      float* dst = o + (long)n * D + c0;
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(r * (v[i] - mu[i]), r * (v[i + 1] - mu[i + 1]),
+                                                          r * (v[i + 2] - mu[i + 2]), r * (v[i + 3] - mu[i + 3]));
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 weighted_center_kernel(const T* __restrict__ X, long strideX, const float* __restrict__ W,
@@ -127,22 +204,36 @@ procrustes_grad_prep_kernel(float* __restrict__ YA, float* __restrict__ YB,
   const float* fa = IA + (long)s * stride_i;
   const float* fb = IB + (long)s * stride_i;
   const float tot = totals[s];
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+  // pi[n] = sum_j pic[j] IA[j,n] IB[j,n]: 4 groups of 128 threads split j, each thread one n
+  // per pass (coalesced along n), partials folded through shared memory
+  __shared__ float pis[4][128];
+  const int tn = threadIdx.x & 127, tg = threadIdx.x >> 7;
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    const int n = n0 + tn;
     float pi = 0.f;
-    for (int j = 0; j < rq; ++j)
-      pi = fmaf(fb[(long)j * ldi + n] * fa[(long)j * ldi + n], pic[(long)s * rq + j], pi);
-    const float wn = w[(long)s * N + n];
-    gw[(long)s * N + n] = ((ks[(long)s * N + n] + kt[(long)s * N + n] - 2.f * pi) / wn - f) / tot;
+    if (n < N)
+      for (int j = tg; j < rq; j += 4)
+        pi = fmaf(fb[(long)j * ldi + n] * fa[(long)j * ldi + n], pic[(long)s * rq + j], pi);
+    pis[tg][tn] = pi;
+    __syncthreads();
+    if (tg == 0 && n < N) {
+      pi = (pis[0][tn] + pis[1][tn]) + (pis[2][tn] + pis[3][tn]);
+      const float wn = w[(long)s * N + n];
+      gw[(long)s * N + n] = ((ks[(long)s * N + n] + kt[(long)s * N + n] - 2.f * pi) / wn - f) / tot;
+    }
+    __syncthreads();
   }
   float* ya = YA ? YA + (long)s * stride_y : nullptr;
   float* yb = YB ? YB + (long)s * stride_y : nullptr;
   if (!ya && !yb) return;
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
-    const int r = e / N, c = e - r * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < N; r += nw) {
     const float sc = 2.f * sqrtf(w[(long)s * N + r]);
-    const float id = (r == c) ? 1.f : 0.f;
-    if (ya) ya[(long)r * ldy + c] = sc * (id - ya[(long)r * ldy + c]);
-    if (yb) yb[(long)r * ldy + c] = sc * (id - yb[(long)r * ldy + c]);
+    for (int c = lane; c < N; c += 32) {
+      const float id = (r == c) ? 1.f : 0.f;
+      if (ya) ya[(long)r * ldy + c] = sc * (id - ya[(long)r * ldy + c]);
+      if (yb) yb[(long)r * ldy + c] = sc * (id - yb[(long)r * ldy + c]);
+    }
   }
 }
 
@@ -209,6 +300,23 @@ extern "C" int basd_weighted_center(const void* X, int dtype, long stride_x, con
                                     long stride_w, int N, int D, float* out, long stride_o,
                                     int batch, void* stream) {
   if (batch <= 0) return 0;
+  constexpr int CW = 128;                                 // columns per block
+  const bool aligned = (D % 8 == 0) && (stride_x % 8 == 0) && (stride_o % 4 == 0) &&
+                       !((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(out)) & 15);
+  if (aligned && batch <= 65535) {
+    dim3 grid(batch, (D + CW - 1) / CW);
+    if (dtype == BASD_DTYPE_BF16) {
+      const size_t dyn = ((size_t)2 * N + (size_t)(256 / (CW / 8)) * CW) * sizeof(float);
+      weighted_center_vec_kernel<__nv_bfloat16, CW><<<grid, 256, dyn, ST>>>(
+          (const __nv_bfloat16*)X, stride_x, W, stride_w, N, D, out, stride_o);
+    } else {
+      const size_t dyn = ((size_t)2 * N + (size_t)(256 / (CW / 4)) * CW) * sizeof(float);
+      weighted_center_vec_kernel<float, CW><<<grid, 256, dyn, ST>>>((const float*)X, stride_x, W,
+                                                                    stride_w, N, D, out, stride_o);
+    }
+    BASD_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t dyn = (size_t)2 * N * sizeof(float);
   if (dtype == BASD_DTYPE_BF16)
     weighted_center_kernel<__nv_bfloat16><<<batch, 256, dyn, ST>>>(
