@@ -164,6 +164,15 @@ int basd_gemm_tc3_supported(int M, int N, int K, int lda, int ldb, int ldc, long
 int basd_gemm_tc3_batched(int ta, int tb, int M, int N, int K, const float* A, int lda, long sa,
                           const float* B, int ldb, long sb, float* C, int ldc, long sc, int batch,
                           float alpha, const float* alpha_dev, void* stream);
+/* Extended form: C = alpha * alpha_dev[0] * (op(A) op(B) - 1 col_sub^T).  a_dtype BF16 (ta = 0;
+ * K, lda, sa multiples of 8): bf16 tokens feed the tensor cores exactly (bf16 is a subset of TF32,
+ * two MMAs per K step); c_dtype BF16 stores the result in the token dtype; col_sub (N floats,
+ * nullable) = mu^T B turns the product into (A - 1 mu^T) B -- the token centring of
+ * layer_selector.py:90-91 applied in the epilogue. */
+int basd_gemm_tc3_batched_ex(int ta, int tb, int M, int N, int K, const void* A, int a_dtype, int lda,
+                             long sa, const float* B, int ldb, long sb, void* C, int c_dtype, int ldc,
+                             long sc, int batch, float alpha, const float* alpha_dev,
+                             const float* col_sub, void* stream);
 
 /* ---- Procrustes glue (procrustes.cu) ------------------------------------------------ */
 

@@ -67,6 +67,28 @@ def test_gemm_tc3_matches_fp64_at_fp32_accuracy(ta, tb, m, n, k):
     assert err < 8 * err_simt + 1e-7, (float(err), float(err_simt))
 
 
+@pytest.mark.parametrize("a_dtype,c_dtype", [(torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32),
+                                             (torch.float32, torch.bfloat16)])
+def test_gemm_tc3_extended_bf16_operand_column_shift_bf16_output(a_dtype, c_dtype):
+    """(A - 1 mu^T) B with bf16 tokens as the A operand, the centring applied in the epilogue
+    and the result stored in the token dtype (selector backward, layer_selector.py:90-91)."""
+    eng = _eng()
+    torch.manual_seed(4)
+    m, n, k = 1000, 384, 384
+    a = (torch.randn(m, k, device=DEV) + 0.7).to(a_dtype)
+    w = torch.randn(k, n, device=DEV) / k ** 0.5
+    mu = a.float().mean(dim=0)
+    shift = (mu.double() @ w.double()).float()
+    c = torch.full((m, n), float("nan"), device=DEV, dtype=c_dtype)
+    alpha_dev = torch.tensor([0.25], device=DEV)
+    assert eng.gemm_tc_ex(0, 0, m, n, k, a, k, 0, w, n, 0, c, n, 0, 1, alpha=2.0, alpha_dev=alpha_dev,
+                          col_sub=shift)
+    ref = 0.5 * ((a.double() - mu.double()) @ w.double())
+    tol = 2e-2 if c_dtype == torch.bfloat16 else 2e-5
+    assert torch.isfinite(c.float()).all()
+    assert (c.double() - ref).abs().max() < tol * ref.abs().max()
+
+
 def test_sgemm_bf16_a_with_shift_and_shared_operand():
     eng = _eng()
     torch.manual_seed(1)

@@ -63,6 +63,23 @@ def sgemm(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch=1, alpha=1.
          float(beta), stream())
 
 
+def gemm_tc_ex(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch=1, alpha=1.0, alpha_dev=None,
+               col_sub=None) -> bool:
+    """Extended tcgen05 GEMM: A may be bf16 (ta = 0), C may be bf16, optional column shift
+    (C = alpha (A B - 1 col_sub^T)).  Returns False (nothing launched) when the shape or the
+    alignment is not accepted, so that the caller takes its SIMT route."""
+    a_bf16 = a.dtype == torch.bfloat16
+    if (not TC_GEMM or min(m, n) < 32 or k < 16 or batch > 65535
+            or ((a.data_ptr() | b.data_ptr() | c.data_ptr()) & 15)
+            or not nat.load().basd_gemm_tc3_supported(m, n, k, lda, ldb, ldc, sa, sb, sc)
+            or (a_bf16 and (ta or k % 8 or lda % 8 or sa % 8))):
+        return False
+    call("basd_gemm_tc3_batched_ex", int(ta), int(tb), m, n, k, ptr(a), nat.dtype_code(a), lda, sa,
+         ptr(b), ldb, sb, ptr(c), nat.dtype_code(c), ldc, sc, batch, float(alpha), ptr(alpha_dev),
+         ptr(col_sub), stream())
+    return True
+
+
 def token_gram(tokens: torch.Tensor, gram: torch.Tensor, colsum: torch.Tensor):
     """gram (D,D) = X^T X, colsum (D) = X^T 1 for X = tokens.reshape(-1, D)."""
     d = tokens.shape[-1]
@@ -455,10 +472,17 @@ def procrustes_backward(students, teachers, stats: Stats, pro: ProcrustesState,
     go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
     scale = 1.0 / (e * b)                                # d geo / d f_{i,b}
     if pro.m_a is not None:
-        grad_s = _f32(e, b, n, d_s, device=dev)
-        sgemm(0, 0, n, d_s, n, pro.m_a, n, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
-              alpha=scale, alpha_dev=go, tc=True)
-        outs = [_cast_like(grad_s[i], s) for i, s in enumerate(students)]
+        sdt = students[0].dtype
+        grad_s = torch.empty(e, b, n, d_s, dtype=sdt, device=dev)
+        if all(s.dtype == sdt for s in students) and gemm_tc_ex(
+                0, 0, n, d_s, n, pro.m_a, n, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
+                alpha=scale, alpha_dev=go):
+            outs = [grad_s[i] for i in range(e)]           # written in the token dtype by the epilogue
+        else:
+            grad_s = _f32(e, b, n, d_s, device=dev)
+            sgemm(0, 0, n, d_s, n, pro.m_a, n, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
+                  alpha=scale, alpha_dev=go, tc=True)
+            outs = [_cast_like(grad_s[i], s) for i, s in enumerate(students)]
     else:
         g_a = pro.g_a.view(e, b, n, d_s)
         outs = []
@@ -530,7 +554,14 @@ def selector_backward(students, sel: SelectorState, proj_s, log_temps, d_weights
     w_prime = omega
     sgemm(0, 0, d_s, d_s, d_s, t3, d_s, dd, proj_s, d_s, 0, w_prime, d_s, dd, e)      # . P
     outs = []
+    shift_dot = _f32(e, d_s, device=dev)                  # mu_i^T W'_i: the centring folded into the epilogue
     for i, s in enumerate(students):
+        sgemm(0, 0, 1, d_s, d_s, sel.mean_s[i], d_s, 0, w_prime[i], d_s, 0, shift_dot[i], d_s, 0, 1)
+        out = torch.empty(s.shape, dtype=s.dtype, device=dev)
+        if gemm_tc_ex(0, 0, b * n, d_s, d_s, s, d_s, 0, w_prime[i], d_s, 0, out, d_s, 0, 1,
+                      col_sub=shift_dot[i]):
+            outs.append(out)
+            continue
         g32 = _f32(b, n, d_s, device=dev)
         sgemm(0, 0, b * n, d_s, d_s, s, d_s, 0, w_prime[i], d_s, 0, g32, d_s, 0, 1,
               a_shift=sel.mean_s[i])

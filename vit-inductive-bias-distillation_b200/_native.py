@@ -55,6 +55,8 @@ _SIG = {
     "basd_geo_reduce": [_p, _i, _i, _p, _i, _p, _p, _p],
     "basd_gemm_tc3_supported": [_i, _i, _i, _i, _i, _i, _l, _l, _l],
     "basd_gemm_tc3_batched": [_i, _i, _i, _i, _i, _p, _i, _l, _p, _i, _l, _p, _i, _l, _i, _f, _p, _p],
+    "basd_gemm_tc3_batched_ex": [_i, _i, _i, _i, _i, _p, _i, _i, _l, _p, _i, _l, _p, _i, _i, _l, _i, _f, _p,
+                                 _p, _p],
     "basd_cast_out": [_p, _p, _i, _l, _p],
 }
 _RET = {"basd_token_gram_simt_workspace_floats": _l}

@@ -189,6 +189,40 @@ __device__ __forceinline__ void store_mncontig(const float4 (&v)[CNT], int R, ui
   }
 }
 
+// bf16 A operand (row-major R x K, K contiguous): one 128-bit load = 8 consecutive k of one row;
+// bf16 is a subset of TF32, so hi is exact, lo is zero and its MMA is skipped.
+// Item f = ptid + u * PRODUCERS (u < 2): row = f / 4, octet = f % 4.
+__device__ __forceinline__ void issue_kcontig_bf16(float4 (&v)[4], const __nv_bfloat16* __restrict__ g,
+                                                   int ld, int r0, int row_limit, int k0, int K,
+                                                   int ptid) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int f = ptid + u * PRODUCERS;
+    const int row = f >> 2, oc = f & 3;
+    const int gr = r0 + row, gk = k0 + oc * 8;
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (gr < row_limit && gk < K)
+      raw = __ldg(reinterpret_cast<const uint4*>(g + static_cast<long>(gr) * ld + gk));
+    v[u] = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
+                       __uint_as_float(raw.w));
+  }
+}
+__device__ __forceinline__ void store_kcontig_bf16(const float4 (&v)[4], uint8_t* hi, int ptid) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int f = ptid + u * PRODUCERS;
+    const int row = f >> 2, oc = f & 3;
+    const uint32_t w[4] = {__float_as_uint(v[u].x), __float_as_uint(v[u].y), __float_as_uint(v[u].z),
+                           __float_as_uint(v[u].w)};
+    const float4 lo4 = make_float4(__uint_as_float(w[0] << 16), __uint_as_float(w[0] & 0xffff0000u),
+                                   __uint_as_float(w[1] << 16), __uint_as_float(w[1] & 0xffff0000u));
+    const float4 hi4 = make_float4(__uint_as_float(w[2] << 16), __uint_as_float(w[2] & 0xffff0000u),
+                                   __uint_as_float(w[3] << 16), __uint_as_float(w[3] & 0xffff0000u));
+    *reinterpret_cast<float4*>(hi + sw_off(row, oc * 8)) = lo4;        // k .. k+3
+    *reinterpret_cast<float4*>(hi + sw_off(row, oc * 8 + 4)) = hi4;    // k+4 .. k+7
+  }
+}
+
 constexpr int A_ITEMS = TM * 8 / PRODUCERS;             // 4 float4 per producer thread
 constexpr int B_ITEMS = 256 * 8 / PRODUCERS;            // 8 (BN <= 256)
 
@@ -199,6 +233,9 @@ struct Params {
   int ta, tb;             // 1: the operand is stored with its contraction index as the slow dimension
   int BN, tiles_n, stages;
   float alpha; const float* alpha_dev;
+  int a_bf16;              // A is bf16 (ta = 0 only): exact in TF32, no lo term
+  const float* col_sub;    // optional (N): C = alpha (acc - col_sub[col])  -- (A - 1 mu^T) B with col_sub = mu^T B
+  int c_bf16;              // store C as bf16
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -245,7 +282,9 @@ gemm_tc3_kernel(const Params p) {
     float4 va[2][A_ITEMS], vb[2][B_ITEMS];
     auto issue = [&](int set, int kb) {
       const int k0 = kb * KS;
-      if (p.ta) issue_mncontig<A_ITEMS>(va[set], A, p.lda, m0, TM, p.M, k0, p.K, ptid);
+      if (p.a_bf16) issue_kcontig_bf16(va[set], reinterpret_cast<const __nv_bfloat16*>(p.A) + prob * p.sa,
+                                       p.lda, m0, p.M, k0, p.K, ptid);
+      else if (p.ta) issue_mncontig<A_ITEMS>(va[set], A, p.lda, m0, TM, p.M, k0, p.K, ptid);
       else      issue_kcontig<A_ITEMS>(va[set], A, p.lda, m0, TM, p.M, k0, p.K, ptid);
       if (p.tb) issue_kcontig<B_ITEMS>(vb[set], B, p.ldb, n0, p.BN, p.N, k0, p.K, ptid);
       else      issue_mncontig<B_ITEMS>(vb[set], B, p.ldb, n0, p.BN, p.N, k0, p.K, ptid);
@@ -258,7 +297,8 @@ gemm_tc3_kernel(const Params p) {
       uint8_t* a_lo = a_hi + A_BYTES;
       uint8_t* b_hi = a_lo + A_BYTES;
       uint8_t* b_lo = b_hi + b_bytes;
-      if (p.ta) store_mncontig<A_ITEMS>(va[set], TM, a_hi, a_lo, ptid);
+      if (p.a_bf16) store_kcontig_bf16(va[set], a_hi, ptid);
+      else if (p.ta) store_mncontig<A_ITEMS>(va[set], TM, a_hi, a_lo, ptid);
       else      store_kcontig<A_ITEMS>(va[set], TM, a_hi, a_lo, ptid);
       if (p.tb) store_kcontig<B_ITEMS>(vb[set], p.BN, b_hi, b_lo, ptid);
       else      store_mncontig<B_ITEMS>(vb[set], p.BN, b_hi, b_lo, ptid);
@@ -293,8 +333,9 @@ gemm_tc3_kernel(const Params p) {
       for (int k = 0; k < ksteps; ++k) {
         const uint64_t dah = make_desc(a_hi + k * 32), dal = make_desc(a_lo + k * 32);
         const uint64_t dbh = make_desc(b_hi + k * 32), dbl = make_desc(b_lo + k * 32);
-        umma_tf32(tmem_base, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+        const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
+        if (!p.a_bf16) umma_tf32(tmem_base, dal, dbh, idesc, acc0);
+        umma_tf32(tmem_base, dah, dbl, idesc, p.a_bf16 ? acc0 : 1u);
         umma_tf32(tmem_base, dah, dbh, idesc, 1u);
       }
       umma_commit(&empty_bar[s]);                       // frees the stage when the MMAs retire
@@ -322,13 +363,35 @@ gemm_tc3_kernel(const Params p) {
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (row < p.M) {
-        float* dst = C + static_cast<long>(row) * p.ldc + n0 + c0;
+        float o[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (c0 + 4 * i < ncols)
-            *reinterpret_cast<float4*>(dst + 4 * i) =
-                make_float4(alpha * __uint_as_float(v[4 * i]), alpha * __uint_as_float(v[4 * i + 1]),
-                            alpha * __uint_as_float(v[4 * i + 2]), alpha * __uint_as_float(v[4 * i + 3]));
+        for (int i = 0; i < 16; ++i) {
+          float a = __uint_as_float(v[i]);
+          if (p.col_sub && c0 + i < ncols) a -= p.col_sub[n0 + c0 + i];
+          o[i] = alpha * a;
+        }
+        if (p.c_bf16) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + prob * p.sc +
+                               static_cast<long>(row) * p.ldc + n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (c0 + 4 * i < ncols) {
+              const __nv_bfloat162 lo2 = __floats2bfloat162_rn(o[4 * i], o[4 * i + 1]);
+              const __nv_bfloat162 hi2 = __floats2bfloat162_rn(o[4 * i + 2], o[4 * i + 3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&lo2);
+              pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
+              *reinterpret_cast<uint2*>(dst + 4 * i) = pk;
+            }
+          }
+        } else {
+          float* dst = C + static_cast<long>(row) * p.ldc + n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (c0 + 4 * i < ncols)
+              *reinterpret_cast<float4*>(dst + 4 * i) =
+                  make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
         }
       }
     }
@@ -353,13 +416,16 @@ extern "C" int basd_gemm_tc3_supported(int M, int N, int K, int lda, int ldb, in
          (sc & 3) == 0;
 }
 
-// C[b] (M x N, pitch ldc) = alpha * alpha_dev[0] * op(A[b]) op(B[b]);  op as in basd_sgemm_batched:
-// ta = 0: A stored M x K, ta = 1: stored K x M;  tb = 0: B stored K x N, tb = 1: stored N x K.
-// All pointers 16-byte aligned, all pitches / strides multiples of 4 floats.
-extern "C" int basd_gemm_tc3_batched(int ta, int tb, int M, int N, int K, const float* A, int lda,
-                                     long sa, const float* B, int ldb, long sb, float* C, int ldc,
-                                     long sc, int batch, float alpha, const float* alpha_dev,
-                                     void* stream) {
+// C[b] (M x N, pitch ldc) = alpha * alpha_dev[0] * (op(A[b]) op(B[b]) - 1 col_sub^T);  op as in
+// basd_sgemm_batched: ta = 0: A stored M x K, ta = 1: stored K x M;  tb = 0: B stored K x N,
+// tb = 1: stored N x K.  a_dtype = BASD_DTYPE_BF16 needs ta = 0 and K, lda, sa multiples of 8;
+// c_dtype = BASD_DTYPE_BF16 stores bf16.  col_sub (N floats) may be null.
+// All pointers 16-byte aligned, all pitches / strides multiples of 4 elements.
+extern "C" int basd_gemm_tc3_batched_ex(int ta, int tb, int M, int N, int K, const void* A,
+                                        int a_dtype, int lda, long sa, const float* B, int ldb,
+                                        long sb, void* C, int c_dtype, int ldc, long sc, int batch,
+                                        float alpha, const float* alpha_dev, const float* col_sub,
+                                        void* stream) {
   using namespace basd;
   using namespace basd::tc3;
   if (batch <= 0 || M <= 0 || N <= 0) return 0;
@@ -367,13 +433,18 @@ extern "C" int basd_gemm_tc3_batched(int ta, int tb, int M, int N, int K, const 
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
        reinterpret_cast<uintptr_t>(C)) & 15)
     return -3;
+  const int a_bf16 = a_dtype == BASD_DTYPE_BF16;
+  if (a_bf16 && (ta || (K & 7) || (lda & 7) || (sa & 7))) return -3;
   if (batch > 65535) return -4;
   Params p;
-  p.A = A; p.B = B; p.C = C;
+  p.A = static_cast<const float*>(A); p.B = B; p.C = static_cast<float*>(C);
   p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sa = sa; p.sb = sb; p.sc = sc;
   p.ta = ta ? 1 : 0;
   p.tb = tb ? 1 : 0;
+  p.a_bf16 = a_bf16;
+  p.col_sub = col_sub;
+  p.c_bf16 = c_dtype == BASD_DTYPE_BF16;
   const int n_tiles = (N + 255) / 256;
   int bn = (N + n_tiles - 1) / n_tiles;
   bn = (bn + 15) & ~15;
@@ -392,4 +463,12 @@ extern "C" int basd_gemm_tc3_batched(int ta, int tb, int M, int N, int K, const 
   gemm_tc3_kernel<<<grid, THREADS, dyn, (cudaStream_t)stream>>>(p);
   BASD_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int basd_gemm_tc3_batched(int ta, int tb, int M, int N, int K, const float* A, int lda,
+                                     long sa, const float* B, int ldb, long sb, float* C, int ldc,
+                                     long sc, int batch, float alpha, const float* alpha_dev,
+                                     void* stream) {
+  return basd_gemm_tc3_batched_ex(ta, tb, M, N, K, A, BASD_DTYPE_F32, lda, sa, B, ldb, sb, C,
+                                  BASD_DTYPE_F32, ldc, sc, batch, alpha, alpha_dev, nullptr, stream);
 }
