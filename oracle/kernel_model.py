@@ -214,6 +214,8 @@ def procrustes_sample(s_tok, t_tok, w, *, sv_floor: float = 2.5e-4, rel_tol: flo
     b = root * (t_tok - (w.unsqueeze(1) * t_tok).sum(0, keepdim=True))
     diag_s, diag_t = (a * a).sum(dim=1), (b * b).sum(dim=1)
     direct_s, direct_t = a.shape[1] <= n, b.shape[1] <= n
+    if direct_s != direct_t and (b.shape[1] if direct_s else a.shape[1]) <= 2 * n:
+        direct_s = direct_t = True                        # see _engine.procrustes_forward
     f_s = a if direct_s else pivoted_cholesky(a @ a.T, rel_tol)
     f_t = b if direct_t else pivoted_cholesky(b @ b.T, rel_tol)
     floor = direct_sv_floor if (direct_s and direct_t) else sv_floor

@@ -35,12 +35,16 @@ def _compare(work, seed=0, temps=None, cos_tol=0.999):
 
 def test_no_cls_multilayer_downsampled_teacher_two_points():
     # ViT teacher without CLS token, more teacher tokens than student tokens (256 -> 196), E = 2.
-    # D_s = 192 <= N = 196 < D_t = 384: direct student side, Gram teacher side.  The 1e-2..1 token
-    # spectrum of these near-square samples puts ~10 singular directions below the sqrt(eps) floor
-    # of the Gram side; the reference keeps their unit-gain polar terms, so the cosine bound here
-    # is 0.998 (CPU model of the same algorithm: 0.9989).
+    # D_s = 192 <= N = 196 < D_t = 384: the student side is direct and, because D_t <= 2N, the
+    # teacher side is taken direct as well (X = A^T B, no Gram): with a Gram teacher side the
+    # ~10 singular directions below sqrt(eps) were lost to both gradients (cosine 0.9989).
     _compare(_work(n_student=196, n_teacher=256, d_student=192, d_teacher=384, has_cls=False,
-                   num_points=2, batch=4), temps=[0.4, 0.9], cos_tol=0.998)
+                   num_points=2, batch=4), temps=[0.4, 0.9])
+
+
+def test_direct_student_side_with_gram_teacher_side():
+    # D_s = 128 <= N = 196, D_t = 512 > 2N: mixed factors (direct student, pivoted-Cholesky teacher)
+    _compare(_work(n_student=196, n_teacher=196, d_student=128, d_teacher=512, batch=4), cos_tol=0.998)
 
 
 def test_single_extraction_point_and_bf16_tokens():

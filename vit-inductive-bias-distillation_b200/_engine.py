@@ -33,6 +33,7 @@ ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerica
 PROC_SV_FLOOR = 2.5e-4   # Procrustes with a Gram side: below sqrt(eps) * sigma_max the recovered v_j is noise
 # both sides direct (no Gram): q_j = normalise(G p_j) is recovered with noise ~eps*sqrt(K)*sigma_max/sigma_j;
 # measured on B200 (tools/debug_edge.py n256): 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
+MIXED_DIRECT_RATIO = float(_os.environ.get("BASD_MIXED_DIRECT_RATIO", 2.0))
 PROC_SV_FLOOR_DIRECT = float(_os.environ.get("BASD_DIRECT_FLOOR", 3e-5))
 
 
@@ -328,10 +329,10 @@ class _Side:
     pivoted Cholesky of K, stored transposed (r = N rows of length N).  Direct side (D <= N):
     F is the token matrix itself (r = D), no Gram and no squared condition number."""
 
-    def __init__(self, tok: torch.Tensor, n: int):
+    def __init__(self, tok: torch.Tensor, n: int, direct: bool | None = None):
         self.tok = tok
         self.p, self.n, self.d = tok.shape
-        self.direct = self.d <= n
+        self.direct = (self.d <= n) if direct is None else direct
         self.r = self.d if self.direct else n
         dev = tok.device
         self.diag = _f32(self.p, n, device=dev)
@@ -384,8 +385,18 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
          ptr(bm), n * d_t, e * b, stream())
 
     p = e * b
-    side_s = _Side(a.view(p, n, d_s), n)
-    side_t = _Side(bm.view(p, n, d_t), n)
+    # A side is direct when D <= N.  When exactly one side qualifies, the other one is taken direct
+    # as well if its width is at most MIXED_DIRECT_RATIO * N: a Gram factor on one side hides the
+    # singular directions below sqrt(eps) from BOTH gradients (measured: N = 196, D_s = 192,
+    # D_t = 384 gives gradient cosine 0.997 with a Gram teacher side, 0.99999 with X = A^T B), at
+    # the price of Jacobi rows of length D instead of N.
+    direct_s, direct_t = d_s <= n, d_t <= n
+    if direct_s != direct_t:
+        wide = d_t if direct_s else d_s
+        if wide <= MIXED_DIRECT_RATIO * n:
+            direct_s = direct_t = True
+    side_s = _Side(a.view(p, n, d_s), n, direct_s)
+    side_t = _Side(bm.view(p, n, d_t), n, direct_t)
     # q = the side with fewer factor columns: the Jacobi sweep orthogonalises the r_q rows of
     # G = F_q^T F_p (length r_p >= r_q).  Ties keep q = teacher.
     swap = side_t.r > side_s.r
