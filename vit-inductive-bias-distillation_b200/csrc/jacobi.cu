@@ -1230,7 +1230,7 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
   const bool no_oddeven = getenv("BASD_JACOBI_ROUNDROBIN") != nullptr;
   // eight rows per 16-lane group (jacobi_oe8.cu): a quarter of the shared-memory exchange traffic
   static const bool no_oe8 = getenv("BASD_JACOBI_NO_OE8") != nullptr;
-  if (!legacy && !no_oddeven && !no_oe8 && n <= 224 && m <= 224) {
+  if (!legacy && !no_oddeven && !no_oe8 && n <= 256 && m <= 256) {
     const int e = launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st,
                                     0, 1 << 30, rot_out);
     if (e != -100) return e;

@@ -178,7 +178,7 @@ __device__ __forceinline__ void angle_pass(float g_own, float& sn, float& sd, fl
 // four redundant evaluations on all 16 lanes); partner states travel by shuffles (width 16) and
 // the two stored-row multipliers of every pair are broadcast back.
 template <int G, int NF>    // G lanes per group; NF floats per lane per row: columns lane + G j, j < NF
-__global__ void __launch_bounds__(G == 16 ? 448 : 896, 1)
+__global__ void __launch_bounds__(G == 16 ? 512 : 896, 1)
 jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                        const int* __restrict__ dims, float tol, int max_sweeps,
                        int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
@@ -368,14 +368,14 @@ static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const
 
 }  // namespace oe8
 
-// Problems with at most 224 active rows and 224 active columns (the per-sample Procrustes SVDs
+// Problems with at most 256 active rows and 256 active columns (the per-sample Procrustes SVDs
 // and the k x k principal-angle SVDs).  Returns -100 when the shape does not fit.
 int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                       float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                       int dim_hi, int* rot_out) {
   const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
   const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
-  if (cap_n > 224 || cap_m > 224) return -100;
+  if (cap_n > 256 || cap_m > 256) return -100;          // 16 warps x 128 registers per CTA
   // 32 lanes per group: twice the warps per SM for the same work, 72 registers
   static const bool wide = getenv("BASD_JACOBI_OE8_G32") != nullptr;   // measured slower (25.1 vs 19.7 ms at C2): opt-in only
 #define BASD_OE8(NF) \
@@ -386,7 +386,7 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
     if (cap_m <= 128) BASD_OE8W(4);
     if (cap_m <= 160) BASD_OE8W(5);
     if (cap_m <= 192) BASD_OE8W(6);
-    BASD_OE8W(7);
+    if (cap_m <= 224 && cap_n <= 224) BASD_OE8W(7);
   }
   if (cap_m <= 64) BASD_OE8(4);
   if (cap_m <= 96) BASD_OE8(6);
@@ -394,7 +394,8 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
   if (cap_m <= 160) BASD_OE8(10);
   if (cap_m <= 192) BASD_OE8(12);
   if (cap_m <= 208) BASD_OE8(13);
-  BASD_OE8(14);
+  if (cap_m <= 224) BASD_OE8(14);
+  BASD_OE8(16);
 #undef BASD_OE8W
 #undef BASD_OE8
 }
