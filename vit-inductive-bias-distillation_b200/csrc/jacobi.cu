@@ -247,6 +247,121 @@ pivoted_cholesky_left_kernel(const float* __restrict__ Kbase, int n, int ld, lon
   if (rank_out && tid == 0) rank_out[prob] = rank;
 }
 
+// Left-looking, four outputs per thread: thread (part, iq) accumulates rows 4iq..4iq+3 of the new
+// column over the factor rows k = part, part + PARTS, ... with ONE 128-bit load of L[k][4iq..] and
+// one broadcast load of L[k][p] per four FMAs (the one-output kernel above issues two loads per
+// FMA and ncu shows it bound by shared-memory instructions).  PARTS = warps / (npad / 128).
+__global__ void __launch_bounds__(1024, 1)
+pivoted_cholesky_left4_kernel(const float* __restrict__ Kbase, int n, int ld, long strideK,
+                              float* __restrict__ LTbase, int ldl, long strideL, float rel_tol,
+                              int* __restrict__ rank_out, const int* __restrict__ dims) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ unsigned int best_val[2][32];
+  __shared__ int best_idx[2][32];
+  __shared__ float red[32];
+  const int prob = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+  const float* Kg = Kbase + (long)prob * strideK;
+  float* LT = LTbase + (long)prob * strideL;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int npad = (n + 127) & ~127;      // multiple of 128: whole warps of row quads
+  float* Ls = smem;                       // n x npad factor rows (row j = column j of L)
+  float* diag = Ls + (size_t)n * npad;    // npad
+  float* pacc = diag + npad;              // parts x npad partial dot products
+  const int wpp = npad >> 7;              // warps per part (32 lanes x 4 rows = 128 rows per warp)
+  const int parts = nwarp / wpp;
+  const int part = warp / wpp;
+  const int i0 = ((warp % wpp) * 32 + lane) * 4;   // first of the four rows this thread produces
+  const bool worker = part < parts;
+  auto warp_argmax = [](float v, int idx_in, unsigned& vbits, int& idx) {
+    const unsigned bits = __float_as_uint(fmaxf(v, 0.f));
+    vbits = __reduce_max_sync(0xffffffffu, bits);
+    const unsigned who = __ballot_sync(0xffffffffu, bits == vbits);
+    idx = __shfl_sync(0xffffffffu, idx_in, __ffs(who) - 1);
+  };
+  if (tid < 64) { best_val[tid >> 5][tid & 31] = 0u; best_idx[tid >> 5][tid & 31] = 0; }
+  __syncthreads();
+  float dmax = 0.f;
+  {
+    float bv = -1.f;
+    int bi = 0;
+    for (int r = tid; r < npad; r += T) {
+      const float d = r < nn ? Kg[(long)r * ld + r] : -1.f;
+      diag[r] = d;
+      dmax = fmaxf(dmax, d);
+      if (d > bv) { bv = d; bi = r; }
+    }
+    unsigned vb;
+    int ib;
+    warp_argmax(bv, bi, vb, ib);
+    if (lane == 0) { best_val[0][warp] = vb; best_idx[0][warp] = ib; }
+  }
+  dmax = block_max(dmax, red);
+  const float floor_v = rel_tol * dmax;
+  __syncthreads();
+  int rank = 0;
+  for (int j = 0; j < nn; ++j) {
+    unsigned vb;
+    int p;
+    {
+      const unsigned cv = lane < nwarp ? best_val[j & 1][lane] : 0u;
+      const int ci = lane < nwarp ? best_idx[j & 1][lane] : 0;
+      vb = __reduce_max_sync(0xffffffffu, cv);
+      const unsigned who = __ballot_sync(0xffffffffu, cv == vb);
+      p = __shfl_sync(0xffffffffu, ci, __ffs(who) - 1);
+    }
+    const float best = __uint_as_float(vb);
+    if (!(best > floor_v) || !(best > 0.f)) break;           // uniform across the block
+    // pivot row of K (== pivot column by symmetry): in flight while the dot products run
+    const bool finisher = tid < npad;                        // thread i finishes row i
+    float kp = 0.f;
+    if (finisher && tid < nn) kp = __ldg(Kg + (long)p * ld + tid);
+    if (worker) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = part; k < j; k += parts) {
+        const float4 l = *reinterpret_cast<const float4*>(Ls + (size_t)k * npad + i0);
+        const float lp = Ls[(size_t)k * npad + p];
+        acc.x = fmaf(l.x, lp, acc.x); acc.y = fmaf(l.y, lp, acc.y);
+        acc.z = fmaf(l.z, lp, acc.z); acc.w = fmaf(l.w, lp, acc.w);
+      }
+      *reinterpret_cast<float4*>(pacc + (size_t)part * npad + i0) = acc;
+    }
+    __syncthreads();
+    float bv = -1.f;
+    int bi = 0;
+    if (finisher) {
+      const int i = tid;
+      float c = 0.f;
+      const float di = diag[i];
+      if (i < nn && di >= 0.f) {
+        float acc = 0.f;
+        for (int q = 0; q < parts; ++q) acc += pacc[(size_t)q * npad + i];
+        c = (i == p) ? best * rsqrtf(best) : (kp - acc) * rsqrtf(best);
+        const float nd = (i == p) ? -1.f : fmaxf(fmaf(-c, c, di), 0.f);
+        diag[i] = nd;
+        bv = nd;
+        bi = i;
+      }
+      Ls[(size_t)j * npad + i] = c;
+      if (i < nn) LT[(long)j * ldl + i] = c;
+    }
+    {
+      unsigned vbn;
+      int ibn;
+      warp_argmax(bv, bi, vbn, ibn);
+      if (lane == 0) { best_val[(j + 1) & 1][warp] = vbn; best_idx[(j + 1) & 1][warp] = ibn; }
+    }
+    __syncthreads();
+    rank = j + 1;
+  }
+  __syncthreads();
+  for (int e = tid; e < n * n; e += T) {
+    const int r = e / n, c = e - r * n;
+    if (r >= rank || c >= nn) LT[(long)r * ldl + c] = 0.f;
+  }
+  if (rank_out && tid == 0) rank_out[prob] = rank;
+}
+
 // ------------------------------------------------------------------ one-sided Jacobi on rows
 template <int NV>
 __global__ void __launch_bounds__((NV >= 3 ? 512 : 1024), 1)
@@ -1172,6 +1287,24 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
   using namespace basd;
   if (batch <= 0 || n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  {   // left-looking, four outputs per thread: factor rows resident in shared memory
+    const size_t npad = ((size_t)n + 127) & ~(size_t)127;
+    const int wpp = (int)(npad >> 7);
+    int warps = 28 / wpp * wpp;                              // <= 896 threads, whole parts
+    if (warps < wpp) warps = wpp;
+    const int parts = warps / wpp;
+    const size_t dyn4 = ((size_t)n * npad + npad + (size_t)parts * npad) * sizeof(float);
+    static const bool no_left4 = getenv("BASD_CHOL_LEFT1") != nullptr;
+    if (!no_left4 && !getenv("BASD_CHOL_RIGHT") && dyn4 + 2048 <= (size_t)smem_limit() &&
+        warps * 32 <= 1024 && warps * 32 >= (int)npad) {
+      BASD_CUDA(cudaFuncSetAttribute(pivoted_cholesky_left4_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn4));
+      pivoted_cholesky_left4_kernel<<<batch, warps * 32, dyn4, st>>>(K, n, ld, stride_k, LT, ldl,
+                                                                    stride_l, rel_tol, rank_out, dims);
+      BASD_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   {   // left-looking kernel: factor rows resident in shared memory
     constexpr int PARTS = 4;
     const size_t np32 = ((size_t)n + 31) & ~(size_t)31;
