@@ -272,12 +272,17 @@ def run_b200(args):
             ev.record(copy_stream)
         return slot, ev
 
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+
     def e2e_run(n_steps):
         """n_steps fwd+bwd steps from pinned host buffers; the upload of step i+1 overlaps the
-        compute of step i (double buffering, as a training loop prefetches its next batch)."""
+        compute of step i (double buffering, as a training loop prefetches its next batch).
+        Every step's loss is copied to pinned host memory and read by the host; the read of
+        step i happens after step i+1 has been enqueued (a one-step-lagged logging read), so the
+        host's launch work for the next step is not serialised behind the GPU's current one."""
         cur = torch.cuda.current_stream()
         nxt = upload(0)
-        last = None
+        last, pending = None, None
         for i in range(n_steps):
             slot, ev = nxt
             cur.wait_event(ev)
@@ -286,10 +291,16 @@ def run_b200(args):
             st_d = {k: v.detach().requires_grad_(True) for k, v in slot["st"].items()}
             loss = mod(slot["lg"].detach().requires_grad_(True), slot["tg"], st_d, slot["te"], slot["at"])
             loss.backward()
+            loss_host[i % 2].copy_(loss.detach(), non_blocking=True)   # device->host read of the step's result
             done = torch.cuda.Event()
             done.record(cur)
             slot["free"] = done
-            last = float(loss.detach().cpu())          # device->host read of the step's result
+            if pending is not None:
+                pending[0].synchronize()
+                last = float(pending[1])
+            pending = (done, loss_host[i % 2])
+        pending[0].synchronize()
+        last = float(pending[1])
         return last
 
     e2e_steps = max(3, min(args.steps, 6))

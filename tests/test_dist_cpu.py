@@ -6,6 +6,7 @@ global row count, one flat buffer, shards that are slices of the global batch.""
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -89,3 +90,41 @@ def test_shards_are_slices_of_the_global_batch():
         assert torch.equal(torch.cat([lo[3][k], hi[3][k]]), full[3][k])
         assert torch.equal(torch.cat([lo[4][k], hi[4][k]]), full[4][k])
     assert torch.equal(torch.cat([lo[1], hi[1]]), full[1])
+
+
+def _shard_worker(rank, world, port, q, d, out):
+    import torch.distributed as dist
+    from basd_b200 import _engine as eng
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    kmats = torch.randn(q, d, d, generator=g)                       # identical on every rank
+    calls = []
+
+    def solver(k):                                                  # stands in for sym_eig (CUDA)
+        calls.append(k.shape[0])
+        return k.diagonal(dim1=1, dim2=2).contiguous() * 3.0, (k * 2.0 + 1.0).contiguous()
+
+    lam, vt = eng.sharded_sym_eig(kmats, None, world, solver=solver)
+    ok = bool(torch.equal(lam, kmats.diagonal(dim1=1, dim2=2) * 3.0) and torch.equal(vt, kmats * 2.0 + 1.0))
+    if rank == 0:
+        out.put((ok, calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,q", [(2, 16), (3, 16), (4, 5)])
+def test_selector_eigenproblems_are_dealt_to_ranks_and_gathered_back(world, q):
+    """Every rank solves ceil(q / world) of the q identical problems; the all-gather returns them
+    in problem order (the ranks hold bit-identical statistics)."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q, 6, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, calls = out.get()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert ok
+    assert calls == [(q + world - 1) // world]

@@ -69,7 +69,7 @@ class MixingWeights(torch.autograd.Function):
         n_t = step.teachers[0].shape[1]
         step.stats = stats
         step.selector = eng.selector_forward(stats, b * n_s * step.world, b * n_t * step.world,
-                                             step.proj_s, step.proj_t, logt)
+                                             step.proj_s, step.proj_t, logt, step.group, step.world)
         ctx.step = step
         ctx.students = students
         ctx.logt = logt

@@ -29,6 +29,8 @@ CHOL_TOL = 1e-5          # pivoted-Cholesky rank cut (per-sample N x N Grams), r
                          # largest diagonal: just above the fp32 accumulation noise of K
 GRAM_CHOL_TOL = 1e-7     # same for the D x D selector Grams
 SV_FLOOR = 1e-6          # k x k principal-angle SVD: directions below this are dropped
+SHARD_SELECTOR_EIG = _os.environ.get("BASD_NO_SELECTOR_SHARDING") is None
+SHARD_WAVE_CTAS = int(_os.environ.get("BASD_SHARD_WAVE_CTAS", 148))
 ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerically zero in fp32
 PROC_SV_FLOOR = 2.5e-4   # Procrustes with a Gram side: below sqrt(eps) * sigma_max the recovered v_j is noise
 # both sides direct (no Gram): q_j = normalise(G p_j) is recovered with noise ~eps*sqrt(K)*sigma_max/sigma_j;
@@ -149,6 +151,37 @@ def sym_eig(kmats: torch.Tensor):
     return lam, vt
 
 
+def sharded_sym_eig(kmats: torch.Tensor, group, world: int, solver=None):
+    """sym_eig with the problems dealt round-robin to the data-parallel ranks.  After the
+    statistics all-reduce every rank holds bit-identical Grams, and without this every rank would
+    repeat the same L_t + E eigenproblems -- latency-bound work that occupies a few SMs (9 ms of the
+    44 ms C2 step, 110 of 212 ms at C4).  Rank r factors problems r, r + W, ...; one all-gather over
+    NVLink (16 x (D^2 + D) floats = 9.4 MB at C2, 66 MB at C4) hands everyone the full set.  Every
+    problem is solved by one CTA / cluster with a fixed schedule, so the result does not depend on
+    which rank solved it."""
+    solver = sym_eig if solver is None else solver
+    # the problems of one launch run concurrently (one CTA cluster each): dealing them out only
+    # pays once a launch exceeds one wave of the GPU (C4: 28 x 768^2; at C2 the 16 x 384^2 problems
+    # fill 64 of 148 SMs and sharding measured 44.4 vs 44.0 ms per step on 2 GPUs)
+    q_all, d_all = kmats.shape[0], kmats.shape[1]
+    one_wave = q_all * max(1, d_all // 96) <= SHARD_WAVE_CTAS
+    if world <= 1 or SHARD_SELECTOR_EIG is False or (one_wave and solver is sym_eig):
+        return solver(kmats)
+    rank = dist.get_rank(group)
+    q, d, _ = kmats.shape
+    per = (q + world - 1) // world
+    own = torch.arange(per, device=kmats.device) * world + rank
+    own = own.clamp(max=q - 1)                            # ranks short of a problem redo the last one
+    lam_l, vt_l = solver(kmats.index_select(0, own).contiguous())
+    packed = torch.cat([lam_l.reshape(per, -1), vt_l.reshape(per, -1)], dim=1).contiguous()
+    gathered = torch.empty(world * per, d + d * d, dtype=torch.float32, device=kmats.device)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    # gathered row (r * per + s) is problem s * world + r
+    order = (torch.arange(q, device=kmats.device) % world) * per + torch.arange(q, device=kmats.device) // world
+    full = gathered.index_select(0, order)
+    return full[:, :d].contiguous(), full[:, d:].reshape(q, d, d).contiguous()
+
+
 # ---------------------------------------------------------------------------- phases
 @dataclass
 class Stats:
@@ -239,7 +272,8 @@ class SelectorState:
     sweeps: dict = field(default_factory=dict)
 
 
-def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log_temps):
+def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log_temps, group=None,
+                     world: int = 1):
     dev = proj_s.device
     e, d_s, _ = stats.gram_s.shape
     l, d_t, _ = stats.gram_t.shape
@@ -267,7 +301,7 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     kall = _f32(l + e, d_s, d_s, device=dev)
     call("basd_center_gram", ptr(ghat_t), ptr(chat_t), d_s, 1.0 / rows_t, ptr(kall[:l]), l, stream())
     call("basd_center_gram", ptr(ghat_s), ptr(chat_s), d_s, 1.0 / rows_s, ptr(kall[l:]), e, stream())
-    lam, vt = sym_eig(kall)
+    lam, vt = sharded_sym_eig(kall, group, world)
     lam_t, lam_s = lam[:l], lam[l:]
     vt_t, vt_s = vt[:l], vt[l:]
     y_t = _f32(l, d_s, device=dev)                        # y = V^T c_hat per teacher layer
