@@ -155,11 +155,14 @@ def roofline(work, mod, args5, pk, clocks):
     # + rotations actually applied x two rotated rows (6m); sweeps/rotation counts come from the device
     jac_ms = [ms for name, ms in tl if name.startswith("basd_jacobi_rows")]
     jac = []
-    for (tag, n, m, dims, sweeps, rot), ms in zip(jlog, jac_ms):
+    for (tag, n, m, dims, sweeps, rot, row_dims), ms in zip(jlog, jac_ms):
         sw = sweeps.double().cpu()
-        kk = dims.double().cpu() if dims is not None else torch.full_like(sw, float(n))
+        # active rows: square sub-problem size (dims), factor rank (row_dims) or n; row length: dims or m
+        kk = (dims.double().cpu() if dims is not None else
+              row_dims.double().cpu().clamp(max=n) if row_dims is not None else torch.full_like(sw, float(n)))
+        ln = dims.double().cpu() if dims is not None else torch.full_like(sw, float(m))
         visits = float((sw * kk * (kk - 1) / 2).sum())
-        flops = float((sw * kk * (kk - 1) / 2 * 2 * kk).sum() + (rot.double().cpu() * 6 * kk).sum())
+        flops = float((sw * kk * (kk - 1) / 2 * 2 * ln).sum() + (rot.double().cpu() * 6 * ln).sum())
         jac.append({"kernel": f"basd_jacobi_rows[{tag}]", "ms": round(ms, 4), "problems": int(sw.numel()),
                     "n": int(kk.max()), "sweeps_mean": round(float(sw.mean()), 2), "pair_visits": visits,
                     "rotations": float(rot.sum()), "bound": "fp32", "achieved": flops / (ms * 1e-3) / 1e12,

@@ -71,6 +71,12 @@ int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, float* LT, int
 int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                      float tol, int max_sweeps, int* sweeps_out, void* stream);
 
+/* Rank-deficient products G = F_q^T F_p: only the first row_dims[problem] rows are non-zero (the
+ * pivoted-Cholesky rank); sweeps over those rows only.  row_dims may be null (= basd_jacobi_rows). */
+int basd_jacobi_rows_ranked(float* G, int n, int m, int ld, long stride, int batch,
+                            const int* row_dims, float tol, int max_sweeps, int* sweeps_out,
+                            int* rot_out, void* stream);
+
 /* Same, and rot_out[problem] += number of plane rotations applied (for the roofline accounting). */
 int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,
                              const int* dims, float tol, int max_sweeps, int* sweeps_out,

@@ -111,15 +111,26 @@ def pivoted_cholesky(k, lt, rel_tol, dims=None, rank_out=None):
 jacobi_log = None
 
 
-def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi", tol=None):
+def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi", tol=None, row_dims=None):
+    """dims: active leading size of square problems (rows and columns); row_dims: number of
+    leading non-zero rows (rank of the factor the rows come from), all columns active."""
     batch, n, m = g.shape
     tol = JACOBI_TOL if tol is None else tol
+    if row_dims is not None and dims is None:
+        rot = None
+        if jacobi_log is not None:
+            sweeps_out = sweeps_out if sweeps_out is not None else torch.zeros(batch, dtype=torch.int32, device=g.device)
+            rot = torch.zeros(batch, dtype=torch.int32, device=g.device)
+            jacobi_log.append((tag, n, m, None, sweeps_out, rot, row_dims))
+        call("basd_jacobi_rows_ranked", ptr(g), n, m, m, n * m, batch, ptr(row_dims), tol, JACOBI_SWEEPS,
+             ptr(sweeps_out), ptr(rot), stream())
+        return
     if jacobi_log is not None:
         sweeps_out = sweeps_out if sweeps_out is not None else torch.zeros(batch, dtype=torch.int32, device=g.device)
         rot = torch.zeros(batch, dtype=torch.int32, device=g.device)
         call("basd_jacobi_rows_counted", ptr(g), n, m, m, n * m, batch, ptr(dims), tol,
              JACOBI_SWEEPS, ptr(sweeps_out), ptr(rot), stream())
-        jacobi_log.append((tag, n, m, dims, sweeps_out, rot))
+        jacobi_log.append((tag, n, m, dims, sweeps_out, rot, None))
         return
     call("basd_jacobi_rows", ptr(g), n, m, m, n * m, batch, ptr(dims), tol, JACOBI_SWEEPS,
          ptr(sweeps_out), stream())
@@ -370,6 +381,7 @@ class _Side:
         self.r = self.d if self.direct else n
         dev = tok.device
         self.diag = _f32(self.p, n, device=dev)
+        self.rank = None                                 # per-problem factor rank (Gram sides)
         if self.direct:
             call("basd_rowdot", ptr(tok), self.d, n * self.d, ptr(tok), self.d, n * self.d, n, self.d,
                  self.p, ptr(self.diag), stream())
@@ -379,7 +391,8 @@ class _Side:
             sgemm(0, 1, n, n, self.d, tok, self.d, n * self.d, tok, self.d, n * self.d, k, n, n * n, self.p, tc=True)
             call("basd_extract_diag", ptr(k), n, n, n * n, self.p, ptr(self.diag), stream())
             self.fac = _f32(self.p, n, n, device=dev)    # stored as F^T (r x N)
-            pivoted_cholesky(k, self.fac, CHOL_TOL)
+            self.rank = torch.empty(self.p, dtype=torch.int32, device=dev)
+            pivoted_cholesky(k, self.fac, CHOL_TOL, rank_out=self.rank)
             self.ld = n
         self.stride = self.fac.shape[1] * self.fac.shape[2]
 
@@ -443,7 +456,8 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
     g0 = _f32(p, rq, rp, device=dev)
     g0.copy_(g)
     sweeps = torch.zeros(p, dtype=torch.int32, device=dev)
-    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes", tol=PROC_JACOBI_TOL)  # rows -> sigma_j p_j^T
+    # rows -> sigma_j p_j^T; rows of G beyond the rank of a Gram-side F_q are exact zeros
+    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes", tol=PROC_JACOBI_TOL, row_dims=sq.rank)
     rows_normalize(g, g, None, sort=False, square=False, rel_floor=ROW_FLOOR)
     pt = g                                                                # (rq, rp) unit rows
     rows2 = _f32(p, rq, rq, device=dev)

@@ -27,6 +27,7 @@ _SIG = {
     "basd_pivoted_cholesky": [_p, _i, _i, _l, _p, _i, _l, _i, _f, _p, _p, _p],
     "basd_jacobi_rows": [_p, _i, _i, _i, _l, _i, _p, _f, _i, _p, _p],
     "basd_jacobi_rows_counted": [_p, _i, _i, _i, _l, _i, _p, _f, _i, _p, _p, _p],
+    "basd_jacobi_rows_ranked": [_p, _i, _i, _i, _l, _i, _p, _f, _i, _p, _p, _p],
     "basd_rows_normalize": [_p, _i, _i, _i, _l, _p, _i, _l, _p, _i, _i, _i, _f, _p, _p],
     "basd_rowdot": [_p, _i, _l, _p, _i, _l, _i, _i, _i, _p, _p],
     "basd_center_gram": [_p, _p, _i, _f, _p, _i, _p],

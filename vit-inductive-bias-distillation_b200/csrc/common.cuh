@@ -89,6 +89,6 @@ int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial /* >
 // returns -100 when the shape does not fit.
 int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                       float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
-                      int dim_hi, int* rot_out);
+                      int dim_hi, int* rot_out, int rows_only = 0);
 
 }  // namespace basd

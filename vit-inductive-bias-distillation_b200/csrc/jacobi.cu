@@ -1347,6 +1347,26 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
                                   nullptr, stream);
 }
 
+// Rank-deficient factor products (G = F_q^T F_p with a pivoted-Cholesky F_q of rank r): only the
+// first row_dims[problem] rows are non-zero, the others are exact zeros that no rotation touches.
+// The register-resident kernel then sweeps over the active rows only (C3: rank 48 of 196 -> a
+// quarter of the steps); other shapes run the full problem, which gives the same result.
+extern "C" int basd_jacobi_rows_ranked(float* G, int n, int m, int ld, long stride, int batch,
+                                       const int* row_dims, float tol, int max_sweeps,
+                                       int* sweeps_out, int* rot_out, void* stream) {
+  using namespace basd;
+  if (batch <= 0 || n <= 0) return 0;
+  if ((ld & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(G) & 15)) return -3;
+  static const bool no_oe8 = getenv("BASD_JACOBI_NO_OE8") != nullptr;
+  if (row_dims && !no_oe8 && n <= 256 && m <= 256) {
+    const int e = launch_jacobi_oe8(G, n, m, ld, stride, batch, row_dims, tol, max_sweeps, sweeps_out,
+                                    (cudaStream_t)stream, 0, 1 << 30, rot_out, 1);
+    if (e != -100) return e;
+  }
+  return basd_jacobi_rows_counted(G, n, m, ld, stride, batch, nullptr, tol, max_sweeps, sweeps_out,
+                                  rot_out, stream);
+}
+
 // Same, additionally accumulating into rot_out[problem] the number of plane rotations applied
 // (bench.py's roofline leg; only the register-resident kernels count, others leave it untouched).
 extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,

@@ -182,15 +182,19 @@ __global__ void __launch_bounds__(G == 16 ? 512 : 896, 1)
 jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                        const int* __restrict__ dims, float tol, int max_sweeps,
                        int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
-                       int* __restrict__ rot_out) {
+                       int* __restrict__ rot_out, int rows_only) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_scratch[32];
   const int prob = blockIdx.x, tid = threadIdx.x;
-  if (dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;
+  // dims: active leading size of a square problem (rows and columns), or -- rows_only -- the
+  // number of leading non-zero rows of a rank-deficient factor product (all columns active)
+  if (dims && !rows_only && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;
   const int gid = tid / G, gl = tid % G;
   float* Gg = Gbase + (long)prob * stride;
-  const int nn = dims ? min(dims[prob], n) : n;
-  const int mm = dims ? min(dims[prob], m) : m;
+  // rows_only: round the active row count up to even -- the extra (exactly zero) row is the "bye"
+  // of the transposition ordering; an odd count measured one sweep more on full-rank problems
+  const int nn = dims ? min(rows_only ? ((dims[prob] + 1) & ~1) : dims[prob], n) : n;
+  const int mm = (dims && !rows_only) ? min(dims[prob], m) : m;
   const int groups = (nn + R - 1) / R;
   const int cnt = max(0, min(R, nn - gid * R));          // positions of this group that exist
   constexpr int PITCH = NF * G;                          // floats per shared-memory row
@@ -351,8 +355,8 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
 template <int G, int NF>
 static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
                   int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo, int dim_hi,
-                  int* rot_out) {
-  const int cap = (dims && dim_hi < n) ? dim_hi : n;
+                  int* rot_out, int rows_only) {
+  const int cap = (dims && !rows_only && dim_hi < n) ? dim_hi : n;
   int threads = ((cap + R - 1) / R) * G;
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;
@@ -361,7 +365,7 @@ static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_kernel<G, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dyn));
   jacobi_rows_oe8_kernel<G, NF><<<batch, threads, dyn, st>>>(Gm, n, m, ld, stride, dims, tol, max_sweeps,
-                                                          sweeps_out, dim_lo, dim_hi, rot_out);
+                                                          sweeps_out, dim_lo, dim_hi, rot_out, rows_only);
   BASD_LAUNCH_CHECK();
   return 0;
 }
@@ -372,16 +376,16 @@ static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const
 // and the k x k principal-angle SVDs).  Returns -100 when the shape does not fit.
 int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                       float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
-                      int dim_hi, int* rot_out) {
-  const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
-  const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
+                      int dim_hi, int* rot_out, int rows_only) {
+  const int cap_n = (dims && !rows_only && dim_hi < n) ? dim_hi : n;
+  const int cap_m = (dims && !rows_only && dim_hi < m) ? dim_hi : m;
   if (cap_n > 256 || cap_m > 256) return -100;          // 16 warps x 128 registers per CTA
   // 32 lanes per group: twice the warps per SM for the same work, 72 registers
   static const bool wide = getenv("BASD_JACOBI_OE8_G32") != nullptr;   // measured slower (25.1 vs 19.7 ms at C2): opt-in only
 #define BASD_OE8(NF) \
-  return oe8::launch<16, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+  return oe8::launch<16, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out, rows_only)
 #define BASD_OE8W(NF) \
-  return oe8::launch<32, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+  return oe8::launch<32, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out, rows_only)
   if (wide && cap_n > 64) {
     if (cap_m <= 128) BASD_OE8W(4);
     if (cap_m <= 160) BASD_OE8W(5);
