@@ -193,6 +193,8 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
   float* Gg = Gbase + (long)prob * stride;
   // rows_only: round the active row count up to even -- the extra (exactly zero) row is the "bye"
   // of the transposition ordering; an odd count measured one sweep more on full-rank problems
+  // (not for square sub-problems: the rows trade places every step, so the zero row would end up
+  // inside the leading k rows the caller reads back and a real one outside)
   const int nn = dims ? min(rows_only ? ((dims[prob] + 1) & ~1) : dims[prob], n) : n;
   const int mm = (dims && !rows_only) ? min(dims[prob], m) : m;
   const int groups = (nn + R - 1) / R;
