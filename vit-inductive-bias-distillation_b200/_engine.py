@@ -329,8 +329,8 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     wfull = _f32(e * l, d_s, d_s, device=dev)
     gx = _f32(e * l, d_s, d_s, device=dev)
     for i in range(e):
-        sgemm(0, 1, d_s, d_s, d_s, vt_s[i], d_s, 0, vt_t, d_s, dd, wfull[i * l:], d_s, dd, l)
-        sgemm(0, 1, d_s, d_s, d_s, vt_t, d_s, dd, vt_s[i], d_s, 0, gx[i * l:], d_s, dd, l)
+        sgemm(0, 1, d_s, d_s, d_s, vt_s[i], d_s, 0, vt_t, d_s, dd, wfull[i * l:], d_s, dd, l, tc=True)
+        sgemm(0, 1, d_s, d_s, d_s, vt_t, d_s, dd, vt_s[i], d_s, 0, gx[i * l:], d_s, dd, l, tc=True)
     call("basd_mask_block", ptr(gx), ptr(gx), d_s, ptr(dims), e * l, stream())
     sweeps = torch.zeros(e * l, dtype=torch.int32, device=dev)
     jacobi_rows(gx, dims=dims, sweeps_out=sweeps, tag="kxk")
@@ -338,7 +338,7 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     sig = _f32(e * l, d_s, device=dev)
     rows_normalize(gx, uxt, sig, sort=True, square=False, rel_floor=SV_FLOOR, dims=dims)
     vxt = gx                                             # reuse as rows2 = Uxt . X
-    sgemm(0, 0, d_s, d_s, d_s, uxt, d_s, dd, wfull, d_s, dd, vxt, d_s, dd, e * l)
+    sgemm(0, 0, d_s, d_s, d_s, uxt, d_s, dd, wfull, d_s, dd, vxt, d_s, dd, e * l, tc=True)
     rows_normalize(vxt, vxt, sig, sort=False, square=False, rel_floor=SV_FLOOR, dims=dims)
 
     dist_el = _f32(e, l, device=dev)
@@ -596,22 +596,22 @@ def selector_backward(students, sel: SelectorState, proj_s, log_temps, d_weights
     call("basd_scale_rows_dsigma", ptr(uxt), ptr(sel.sig), ptr(sel.lam_t), ptr(sel.ranks),
          ptr(d_dist), d_s, e, l, stream())
     t1 = _f32(e * l, d_s, d_s, device=dev)
-    sgemm(0, 1, d_s, d_s, d_s, sel.wfull, d_s, dd, sel.vxt, d_s, dd, t1, d_s, dd, e * l)
+    sgemm(0, 1, d_s, d_s, d_s, sel.wfull, d_s, dd, sel.vxt, d_s, dd, t1, d_s, dd, e * l, tc=True)
     blk = _f32(e * l, d_s, d_s, device=dev)
-    sgemm(0, 0, d_s, d_s, d_s, t1, d_s, dd, uxt, d_s, dd, blk, d_s, dd, e * l)
+    sgemm(0, 0, d_s, d_s, d_s, t1, d_s, dd, uxt, d_s, dd, blk, d_s, dd, e * l, tc=True)
     omega = _f32(e, d_s, d_s, device=dev)
     call("basd_omega_accumulate", ptr(blk), ptr(sel.lam_s), ptr(sel.ranks), d_s, e, l, ptr(omega),
          stream())
     t2 = _f32(e, d_s, d_s, device=dev)
-    sgemm(1, 0, d_s, d_s, d_s, sel.vt_s, d_s, dd, omega, d_s, dd, t2, d_s, dd, e)     # V Omega
+    sgemm(1, 0, d_s, d_s, d_s, sel.vt_s, d_s, dd, omega, d_s, dd, t2, d_s, dd, e, tc=True)     # V Omega
     d_gram = _f32(e, d_s, d_s, device=dev)
-    sgemm(0, 0, d_s, d_s, d_s, t2, d_s, dd, sel.vt_s, d_s, dd, d_gram, d_s, dd, e)    # . V^T
+    sgemm(0, 0, d_s, d_s, d_s, t2, d_s, dd, sel.vt_s, d_s, dd, d_gram, d_s, dd, e, tc=True)    # . V^T
     w_sym = t2
     call("basd_symmetrize_add", ptr(d_gram), d_s, ptr(w_sym), e, stream())
     t3 = d_gram
-    sgemm(1, 0, d_s, d_s, d_s, proj_s, d_s, 0, w_sym, d_s, dd, t3, d_s, dd, e)        # P^T W
+    sgemm(1, 0, d_s, d_s, d_s, proj_s, d_s, 0, w_sym, d_s, dd, t3, d_s, dd, e, tc=True)        # P^T W
     w_prime = omega
-    sgemm(0, 0, d_s, d_s, d_s, t3, d_s, dd, proj_s, d_s, 0, w_prime, d_s, dd, e)      # . P
+    sgemm(0, 0, d_s, d_s, d_s, t3, d_s, dd, proj_s, d_s, 0, w_prime, d_s, dd, e, tc=True)      # . P
     outs = []
     shift_dot = _f32(e, d_s, device=dev)                  # mu_i^T W'_i: the centring folded into the epilogue
     for i, s in enumerate(students):
