@@ -288,10 +288,8 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     dev = proj_s.device
     e, d_s, _ = stats.gram_s.shape
     l, d_t, _ = stats.gram_t.shape
-    if rows_t < d_s or rows_s < d_s:
-        raise ValueError(
-            f"BASD kernels need at least D_s={d_s} token rows per layer (got {rows_s} student, "
-            f"{rows_t} teacher): the reference's M<D branch (layer_selector.py:14-15) is not built")
+    # rows < D_s (the reference's M < D branch, layer_selector.py:14-15): the M x M Gram it switches
+    # to has the M largest eigenvalues of the D_s x D_s one; the MP kernels take the median over those
     # --- rotate the token-space statistics by the fixed projections (exact in fp32)
     tmp_t = _f32(l, d_s, d_t, device=dev)
     sgemm(0, 0, d_s, d_t, d_t, proj_t, d_t, 0, stats.gram_t, d_t, d_t * d_t, tmp_t, d_t, d_s * d_t, l)

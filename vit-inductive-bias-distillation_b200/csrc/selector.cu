@@ -22,7 +22,10 @@ __global__ void center_gram_kernel(const float* __restrict__ G, const float* __r
 
 // MP rank of each teacher layer from the spectrum of the uncentred second moment
 // (reference: layer_selector.py:8-20 and :74).  lam: (L, D) in any order.
-__global__ void mp_rank_kernel(const float* __restrict__ lam, int D, float aspect /* D/M */,
+// n_eig = min(M, D): with fewer rows than dimensions the reference switches to the M x M Gram
+// (layer_selector.py:14-15), whose spectrum is the n_eig largest eigenvalues of the D x D one --
+// the median is taken over that population (the D - n_eig structural zeros are left out).
+__global__ void mp_rank_kernel(const float* __restrict__ lam, int D, int n_eig, float aspect /* D/M */,
                                int cap, int* __restrict__ ranks, float* __restrict__ edges) {
   extern __shared__ float v[];
   __shared__ float median;
@@ -32,7 +35,7 @@ __global__ void mp_rank_kernel(const float* __restrict__ lam, int D, float aspec
   for (int i = threadIdx.x; i < D; i += blockDim.x) v[i] = l[i];
   if (threadIdx.x == 0) count = 0;
   __syncthreads();
-  const int want = (D - 1) / 2;   // torch.median: lower middle of the ascending order
+  const int want = (D - n_eig) + (n_eig - 1) / 2;   // torch.median: lower middle of the ascending order
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     int below = 0;
     const float mine = v[i];
@@ -87,7 +90,7 @@ __device__ int secular_count(const double* lam, const double* y2, int D, double 
 }
 
 __global__ void mp_rank_secular_kernel(const float* __restrict__ lam_c, const float* __restrict__ y,
-                                       int D, double rho, float aspect, int cap,
+                                       int D, int n_eig, double rho, float aspect, int cap,
                                        int* __restrict__ ranks, float* __restrict__ edges) {
   extern __shared__ double sd[];
   double* lam = sd;          // D
@@ -106,7 +109,7 @@ __global__ void mp_rank_secular_kernel(const float* __restrict__ lam_c, const fl
   for (int j = 0; j < D; ++j) { hi = fmax(hi, lam[j]); ysum += y2[j]; }   // tiny, every thread
   hi = hi + rho * ysum + 1e-30;                       // mu_max <= lam_max + rho |y|^2
   double lo = fmin(0.0, -hi);                         // K_c is PSD up to rounding
-  const int want = D - (D - 1) / 2;                   // lower median = want-th largest
+  const int want = n_eig - (n_eig - 1) / 2;           // lower median of the n_eig largest = want-th largest
   // largest x with #{mu > x} >= want  ==  the want-th largest root
   for (int it = 0; it < 80; ++it) {
     const double mid = 0.5 * (lo + hi);
@@ -291,7 +294,8 @@ extern "C" int basd_center_gram(const float* G, const float* colsum, int D, floa
 extern "C" int basd_mp_rank(const float* lam, int D, long rows, int cap, int* ranks, float* edges,
                             int layers, void* stream) {
   if (layers <= 0) return 0;
-  mp_rank_kernel<<<layers, 256, D * sizeof(float), ST>>>(lam, D, (float)((double)D / (double)rows),
+  mp_rank_kernel<<<layers, 256, D * sizeof(float), ST>>>(lam, D, (int)(rows < D ? rows : D),
+                                                         (float)((double)D / (double)rows),
                                                          cap, ranks, edges);
   BASD_LAUNCH_CHECK();
   return 0;
@@ -301,7 +305,8 @@ extern "C" int basd_mp_rank_secular(const float* lam_c, const float* y, int D, l
                                     int* ranks, float* edges, int layers, void* stream) {
   if (layers <= 0) return 0;
   mp_rank_secular_kernel<<<layers, 128, 2 * D * sizeof(double), ST>>>(
-      lam_c, y, D, 1.0 / (double)rows, (float)((double)D / (double)rows), cap, ranks, edges);
+      lam_c, y, D, (int)(rows < D ? rows : D), 1.0 / (double)rows, (float)((double)D / (double)rows), cap,
+      ranks, edges);
   BASD_LAUNCH_CHECK();
   return 0;
 }

@@ -26,8 +26,6 @@ def marchenko_pastur_rank(features: torch.Tensor) -> int:
     if features.dim() != 2:
         raise ValueError("features must be (M, D)")
     rows, dim = features.shape
-    if rows < dim:
-        raise ValueError("marchenko_pastur_rank: the M < D branch (reference :14-15) is not built")
     x = features.contiguous()
     gram = torch.empty(1, dim, dim, dtype=torch.float32, device=x.device)
     col = torch.empty(dim, dtype=torch.float32, device=x.device)
