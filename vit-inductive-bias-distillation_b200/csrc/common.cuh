@@ -91,4 +91,8 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
                       float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                       int dim_hi, int* rot_out, int rows_only = 0);
 
+int launch_jacobi_oe8_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                              float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                              int dim_hi, int* rot_out);
+
 }  // namespace basd

@@ -1604,6 +1604,13 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
     if (e) return e;
     lo = SMALL + 1;
   }
+  // eight rows per group spread over a cluster (jacobi_oe8.cu): up to 768 rows x 384 columns
+  static const bool no_oe8c = getenv("BASD_JACOBI_NO_OE8_CLUSTER") != nullptr;
+  if (!legacy && !no_oddeven && !no_oe8 && !no_oe8c && m <= 384 && n <= 768) {
+    const int e = launch_jacobi_oe8_cluster(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
+                                            sweeps_out, st, lo, 1 << 30, rot_out);
+    if (e != -100) return e;
+  }
   // register-resident rows spread over a cluster (16 lanes per pair, 48 pairs per CTA)
   static const bool no_oe_cluster = getenv("BASD_JACOBI_L2CLUSTER") != nullptr;
   if (!legacy && !no_oddeven && !no_oe_cluster && quads <= 16 * 7 && n <= 8 * 96) {

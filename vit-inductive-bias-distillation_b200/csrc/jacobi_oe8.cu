@@ -16,7 +16,10 @@
 // Serves the same contract as basd_jacobi_rows (reference: torch.linalg.svd / svdvals /
 // matrix_norm(ord="nuc"), layer_selector.py:92,99 and relational.py:48).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace basd {
 namespace oe8 {
@@ -354,6 +357,265 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster variant (G = 16): the rows of ONE problem are spread over the CTAs of a thread-block
+// cluster, gpc groups of eight rows per CTA (<= 12 groups = 192 threads, so a thread may hold
+// seven 24-float row pieces in registers: 384 columns).  The only cross-CTA traffic is position 0
+// of the first group of the next CTA: the last group of a CTA reads that row through distributed
+// shared memory INTO REGISTERS at the start of the odd step -- the DSMEM latency then overlaps the
+// three register-only pairs -- and writes it back after the rotation.  One hardware cluster
+// barrier per step.  Serves the 384 x 384 selector eigenproblems (4 CTAs per problem).
+template <int ODD>
+__device__ __forceinline__ void angle_pass_ptr(float g_own, float& sn, float& sd, float2* xs_my,
+                                               float2* xs_right, int gl, int cnt, bool cross_ok,
+                                               float tol2, float zero_thr, float& worst, int& nrot,
+                                               float (&T1)[4], float (&T2)[4]) {
+  constexpr int G = 16;
+  const bool owner = gl < R && (gl & 1) == ODD;
+  const bool from_smem_x = !ODD && gl == 0;
+  const bool from_smem_y = ODD && gl == R - 1;
+  const float pn = __shfl_down_sync(0xffffffffu, sn, 1, G);
+  const float pd = __shfl_down_sync(0xffffffffu, sd, 1, G);
+  RowState sx{sn, sd}, sy{pn, pd};
+  if (from_smem_x) { const float2 v = *xs_my; sx.n = v.x; sx.d = v.y; }
+  if (from_smem_y) { const float2 v = *xs_right; sy.n = v.x; sy.d = v.y; }
+  const bool valid = owner && (from_smem_y ? cross_ok : (gl + 1 < cnt));
+  float t1, t2;
+  angle(g_own, sx, sy, valid, tol2, zero_thr, worst, nrot, t1, t2);
+  if (from_smem_x) *xs_my = make_float2(sx.n, sx.d);
+  else if (owner) { sn = sx.n; sd = sx.d; }
+  if (from_smem_y && valid) *xs_right = make_float2(sy.n, sy.d);
+  const float rn = __shfl_up_sync(0xffffffffu, sy.n, 1, G);
+  const float rd = __shfl_up_sync(0xffffffffu, sy.d, 1, G);
+  const bool receiver = gl >= 1 && gl < R && ((gl - 1) & 1) == ODD;
+  if (receiver) { sn = rn; sd = rd; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    T1[k] = __shfl_sync(0xffffffffu, t1, 2 * k + ODD, G);
+    T2[k] = __shfl_sync(0xffffffffu, t2, 2 * k + ODD, G);
+  }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(192, 1)
+jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                               const int* __restrict__ dims, float tol, int max_sweeps,
+                               int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
+                               int* __restrict__ rot_out) {
+  constexpr int G = 16;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = cluster.num_blocks(), crank = cluster.block_rank();
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red_scratch[32];
+  __shared__ int cflag[2];
+  const int prob = blockIdx.x / csize, tid = threadIdx.x;
+  if (dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;     // whole cluster exits together
+  const int gpc = blockDim.x / G;
+  const int lgid = tid / G, gl = tid % G;
+  const int gid = crank * gpc + lgid;
+  float* Gg = Gbase + (long)prob * stride;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
+  const int groups = (nn + R - 1) / R;
+  const int cnt = max(0, min(R, nn - gid * R));
+  constexpr int PITCH = NF * G;
+  const int nslots = gpc + 1;                            // + a spare nobody pairs with
+  float2* xs = reinterpret_cast<float2*>(smem + (size_t)nslots * PITCH);
+  float* my_row = smem + (size_t)lgid * PITCH + gl;
+  float2* xs_my = xs + lgid;
+  float* right_row = smem + (size_t)(lgid + 1) * PITCH + gl;
+  float2* xs_right = xs + lgid + 1;
+  if (lgid + 1 == gpc && crank + 1 < csize) {            // first group of the next CTA (DSMEM)
+    right_row = cluster.map_shared_rank(smem, crank + 1) + gl;
+    xs_right = cluster.map_shared_rank(xs, crank + 1);
+  }
+  int* flag0 = cluster.map_shared_rank(cflag, 0);
+  auto wide_max = [&](float v, int which) {
+    v = block_max(v, red_scratch);
+    if (tid == 0) atomicMax(flag0 + which, __float_as_int(v));     // non-negative floats order as ints
+    cluster.sync();
+    return __int_as_float(flag0[which]);
+  };
+
+  float r[R - 1][NF];
+  float sn = 0.f, sd = 1.f;
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    const int c = gl + G * j;
+    my_row[G * j] = (cnt > 0 && c < mm) ? Gg[(long)(gid * R) * ld + c] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < R - 1; ++i) {
+    const int row = gid * R + i + 1;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const int c = gl + G * j;
+      r[i][j] = (i + 1 < cnt && c < mm) ? Gg[(long)row * ld + c] : 0.f;
+    }
+  }
+  const bool cross_ok = (cnt == R) && (gid + 1 < groups);
+  const float tol2 = tol * tol;
+  int nrot = 0;
+  int sweep = 0;
+  for (; sweep < max_sweeps && nn >= 2; ++sweep) {
+    if (crank == 0 && tid == 0) { cflag[0] = 0; cflag[1] = 0; }
+    cluster.sync();
+    float nrm[R];
+    {
+      const float d0 = sweep ? xs_my->y : 1.f;
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const float v = my_row[G * j] * d0;
+        my_row[G * j] = v;
+        a = fmaf(v, v, a);
+      }
+      nrm[0] = a;
+    }
+#pragma unroll
+    for (int i = 0; i < R - 1; ++i) {
+      const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < NF; ++e) {
+        r[i][e] *= di;
+        a = fmaf(r[i][e], r[i][e], a);
+      }
+      nrm[i + 1] = a;
+    }
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) nrm[i] += __shfl_xor_sync(0xffffffffu, nrm[i], o);
+    }
+    sd = 1.f;
+    sn = 0.f;
+    float mxl = 0.f;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      mxl = fmaxf(mxl, nrm[i]);
+      if (gl == i) sn = nrm[i];
+    }
+    if (gl == 0) *xs_my = make_float2(nrm[0], 1.f);
+    const float mx = wide_max(mxl, 0);                   // (its cluster barrier orders the writes above)
+    const float zero_thr = 1e-14f * mx;
+    float worst = 0.f;
+    for (int step = 0; step < nn; step += 2) {
+      float ga[4], T1[4], T2[4], x0[NF];
+      // ---------------- even step: position 0 comes into registers once, goes back once
+      const bool fold_now = (step & 15) == 0 && step;
+      const float d0 = fold_now ? xs_my->y : 1.f;
+      if (fold_now) __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NF; ++j) x0[j] = my_row[G * j] * d0;
+      if (fold_now) {
+        if (gl == 0) xs_my->y = 1.f;
+#pragma unroll
+        for (int i = 0; i < R - 1; ++i) {
+          const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
+#pragma unroll
+          for (int e = 0; e < NF; ++e) r[i][e] *= di;
+        }
+        sd = 1.f;
+        __syncwarp();
+      }
+      ga[0] = dot_local<NF>(x0, r[0]);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) ga[k] = dot_local<NF>(r[2 * k - 1], r[2 * k]);
+      angle_pass_ptr<0>(reduce4_owner<G>(ga, gl), sn, sd, xs_my, xs_right, gl, cnt, cross_ok, tol2, zero_thr,
+                        worst, nrot, T1, T2);
+      apply<NF>(x0, r[0], 1 < cnt, T1[0], T2[0]);
+#pragma unroll
+      for (int j = 0; j < NF; ++j) my_row[G * j] = x0[j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) apply<NF>(r[2 * k - 1], r[2 * k], 2 * k + 1 < cnt, T1[k], T2[k]);
+      cluster.sync();
+      // ---------------- odd step: the neighbour's position 0 (possibly remote) into registers first
+      if (step + 1 < nn) {
+#pragma unroll
+        for (int j = 0; j < NF; ++j) x0[j] = right_row[G * j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ga[k] = dot_local<NF>(r[2 * k], r[2 * k + 1]);
+        ga[3] = dot_local<NF>(r[R - 2], x0);
+        angle_pass_ptr<1>(reduce4_owner<G>(ga, gl), sn, sd, xs_my, xs_right, gl, cnt, cross_ok, tol2, zero_thr,
+                          worst, nrot, T1, T2);
+        if (cross_ok) {
+          apply<NF>(r[R - 2], x0, true, T1[3], T2[3]);
+#pragma unroll
+          for (int j = 0; j < NF; ++j) right_row[G * j] = x0[j];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) apply<NF>(r[2 * k], r[2 * k + 1], 2 * k + 2 < cnt, T1[k], T2[k]);
+      }
+      cluster.sync();
+    }
+    const float all_worst = wide_max(worst, 1);
+    cluster.sync();                                      // everyone has read the flags before rank 0 resets them
+    if (all_worst < tol) { ++sweep; break; }
+  }
+  {
+    const float d0 = (nn >= 2 && sweep) ? xs_my->y : 1.f;
+    if (cnt > 0) {
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int c = gl + G * j;
+        if (c < mm) Gg[(long)(gid * R) * ld + c] = my_row[G * j] * d0;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < R - 1; ++i) {
+    const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
+    const int row = gid * R + i + 1;
+    if (i + 1 < cnt) {
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int c = gl + G * j;
+        if (c < mm) Gg[(long)row * ld + c] = r[i][j] * di;
+      }
+    }
+  }
+  if (sweeps_out && crank == 0 && tid == 0) sweeps_out[prob] = sweep;
+  if (rot_out) {
+    const float tot = block_sum((float)nrot, red_scratch);
+    if (tid == 0) atomicAdd(rot_out + prob, (int)tot);
+  }
+}
+
+template <int NF>
+static int launch_cluster(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims,
+                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                          int dim_hi, int* rot_out) {
+  constexpr int G = 16, GPC_MAX = 12;                     // 192 threads: up to 255 registers each
+  const int cap = (dims && dim_hi < n) ? dim_hi : n;
+  const int groups = (cap + R - 1) / R;
+  int csize = 1;
+  while (csize < 8 && csize * GPC_MAX < groups) csize <<= 1;
+  if (csize * GPC_MAX < groups) return -100;
+  int gpc = (groups + csize - 1) / csize;
+  gpc = (gpc + 1) & ~1;                                   // whole warps
+  const int threads = gpc * G;
+  const size_t nslots = gpc + 1;
+  const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
+  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_cluster_kernel<NF>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(batch * csize);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_oe8_cluster_kernel<NF>, Gm, n, m, ld, stride, dims, tol,
+                               max_sweeps, sweeps_out, dim_lo, dim_hi, rot_out));
+  return 0;
+}
+
 template <int G, int NF>
 static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
                   int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo, int dim_hi,
@@ -404,6 +666,22 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
   BASD_OE8(16);
 #undef BASD_OE8W
 #undef BASD_OE8
+}
+
+// Cluster variant: up to 768 active rows (8 CTAs x 12 groups x 8 rows) and 384 active columns.
+// Returns -100 when the shape does not fit.
+int launch_jacobi_oe8_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                              float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                              int dim_hi, int* rot_out) {
+  const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
+  const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
+  if (cap_n > 768 || cap_m > 384) return -100;
+#define BASD_OE8C(NF) \
+  return oe8::launch_cluster<NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+  if (cap_m <= 256) BASD_OE8C(16);
+  if (cap_m <= 320) BASD_OE8C(20);
+  BASD_OE8C(24);
+#undef BASD_OE8C
 }
 
 }  // namespace basd
