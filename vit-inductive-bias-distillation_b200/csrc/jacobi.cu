@@ -1611,6 +1611,14 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
                                             sweeps_out, st, lo, 1 << 30, rot_out);
     if (e != -100) return e;
   }
+  // wider allocations with a device-side active size (C4: k ~ 366 of 768): the problems whose
+  // active size fits take the cluster kernel through its size window, the rest fall through
+  if (!legacy && !no_oddeven && !no_oe8 && !no_oe8c && dims && n == m && m > 384 && lo <= 384) {
+    const int e = launch_jacobi_oe8_cluster(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
+                                            sweeps_out, st, lo, 384, rot_out);
+    if (e == 0) lo = 385;
+    else if (e != -100) return e;
+  }
   // register-resident rows spread over a cluster (16 lanes per pair, 48 pairs per CTA)
   static const bool no_oe_cluster = getenv("BASD_JACOBI_L2CLUSTER") != nullptr;
   if (!legacy && !no_oddeven && !no_oe_cluster && quads <= 16 * 7 && n <= 8 * 96) {
