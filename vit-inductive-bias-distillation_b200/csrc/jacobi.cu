@@ -1461,36 +1461,40 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
       return 0;
     }
   }
-  {   // factor rows dealt to a 4-CTA cluster (Grams beyond one SM's shared memory)
-    constexpr int CS = 4;
+  {   // factor rows dealt to a cluster of 4 CTAs -- or 16 (non-portable size, one cluster per GPC) when
+      // a quarter of the factor does not fit one SM's shared memory (768 x 768: 48 rows per CTA)
     const size_t npc = ((size_t)n + 127) & ~(size_t)127;
     const int wpp = (int)(npc >> 7);
     const int warps = 28 / wpp * wpp;
     const int parts = warps > 0 ? warps / wpp : 0;
-    const size_t rows_local = ((size_t)n + CS - 1) / CS;
-    const size_t dync = (rows_local * npc + 3 * npc + (size_t)parts * npc) * sizeof(float);
     static const bool no_chol_cluster = getenv("BASD_CHOL_NO_CLUSTER") != nullptr;
     // few large problems only: with thousands of them one CTA per problem keeps every SM busy
     // (N = 256, 1,024 problems: 91 vs 82 ms per step with the clusters)
-    if (!no_chol_cluster && !getenv("BASD_CHOL_RIGHT") && parts >= 1 && warps * 32 >= (int)npc &&
-        batch * CS <= 2 * sm_count() && dync + 2048 <= (size_t)smem_limit()) {
-      BASD_CUDA(cudaFuncSetAttribute(pivoted_cholesky_left4_cluster_kernel<CS>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dync));
+    const bool eligible = !no_chol_cluster && !getenv("BASD_CHOL_RIGHT") && parts >= 1 &&
+                          warps * 32 >= (int)npc;
+    for (int cs = 4; eligible && cs <= 16; cs *= 4) {
+      const size_t rows_local = ((size_t)n + cs - 1) / cs;
+      const size_t dync = (rows_local * npc + 3 * npc + (size_t)parts * npc) * sizeof(float);
+      if (dync + 2048 > (size_t)smem_limit() || batch * cs > 4 * sm_count()) continue;
+      auto kern = cs == 4 ? pivoted_cholesky_left4_cluster_kernel<4> : pivoted_cholesky_left4_cluster_kernel<16>;
+      BASD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dync));
+      if (cs > 8) BASD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(batch * CS);
+      cfg.gridDim = dim3(batch * cs);
       cfg.blockDim = dim3(warps * 32);
       cfg.dynamicSmemBytes = dync;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = CS;
+      attr[0].val.clusterDim.x = cs;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      BASD_CUDA(cudaLaunchKernelEx(&cfg, pivoted_cholesky_left4_cluster_kernel<CS>, (const float*)K, n, ld,
-                                   stride_k, LT, ldl, stride_l, rel_tol, rank_out, dims));
-      return 0;
+      if (cudaLaunchKernelEx(&cfg, kern, (const float*)K, n, ld, stride_k, LT, ldl, stride_l, rel_tol,
+                             rank_out, dims) == cudaSuccess)
+        return 0;
+      (void)cudaGetLastError();                              // refused cluster shape: try the next route
     }
   }
   const size_t npad = ((size_t)n + 3) & ~(size_t)3;
@@ -1606,10 +1610,11 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
   }
   // eight rows per group spread over a cluster (jacobi_oe8.cu): up to 768 rows x 384 columns
   static const bool no_oe8c = getenv("BASD_JACOBI_NO_OE8_CLUSTER") != nullptr;
-  if (!legacy && !no_oddeven && !no_oe8 && !no_oe8c && m <= 384 && n <= 768) {
+  if (!legacy && !no_oddeven && !no_oe8 && !no_oe8c && (m <= 384 || !dims) && m <= 768 && n <= 768) {
     const int e = launch_jacobi_oe8_cluster(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
                                             sweeps_out, st, lo, 1 << 30, rot_out);
-    if (e != -100) return e;
+    if (e == 0) return 0;                                  // (-100 or a refused non-portable cluster: fall through)
+    (void)cudaGetLastError();
   }
   // wider allocations with a device-side active size (C4: k ~ 366 of 768): the problems whose
   // active size fits take the cluster kernel through its size window, the rest fall through

@@ -365,12 +365,11 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
 // shared memory INTO REGISTERS at the start of the odd step -- the DSMEM latency then overlaps the
 // three register-only pairs -- and writes it back after the rotation.  One hardware cluster
 // barrier per step.  Serves the 384 x 384 selector eigenproblems (4 CTAs per problem).
-template <int ODD>
+template <int G, int ODD>
 __device__ __forceinline__ void angle_pass_ptr(float g_own, float& sn, float& sd, float2* xs_my,
                                                float2* xs_right, int gl, int cnt, bool cross_ok,
                                                float tol2, float zero_thr, float& worst, int& nrot,
                                                float (&T1)[4], float (&T2)[4]) {
-  constexpr int G = 16;
   const bool owner = gl < R && (gl & 1) == ODD;
   const bool from_smem_x = !ODD && gl == 0;
   const bool from_smem_y = ODD && gl == R - 1;
@@ -396,13 +395,12 @@ __device__ __forceinline__ void angle_pass_ptr(float g_own, float& sn, float& sd
   }
 }
 
-template <int NF>
+template <int G, int NF>
 __global__ void __launch_bounds__(192, 1)
 jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                                const int* __restrict__ dims, float tol, int max_sweeps,
                                int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
                                int* __restrict__ rot_out) {
-  constexpr int G = 16;
   cg::cluster_group cluster = cg::this_cluster();
   const int csize = cluster.num_blocks(), crank = cluster.block_rank();
   extern __shared__ __align__(16) float smem[];
@@ -522,7 +520,7 @@ jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, 
       ga[0] = dot_local<NF>(x0, r[0]);
 #pragma unroll
       for (int k = 1; k < 4; ++k) ga[k] = dot_local<NF>(r[2 * k - 1], r[2 * k]);
-      angle_pass_ptr<0>(reduce4_owner<G>(ga, gl), sn, sd, xs_my, xs_right, gl, cnt, cross_ok, tol2, zero_thr,
+      angle_pass_ptr<G, 0>(reduce4_owner<G>(ga, gl), sn, sd, xs_my, xs_right, gl, cnt, cross_ok, tol2, zero_thr,
                         worst, nrot, T1, T2);
       apply<NF>(x0, r[0], 1 < cnt, T1[0], T2[0]);
 #pragma unroll
@@ -537,7 +535,7 @@ jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, 
 #pragma unroll
         for (int k = 0; k < 3; ++k) ga[k] = dot_local<NF>(r[2 * k], r[2 * k + 1]);
         ga[3] = dot_local<NF>(r[R - 2], x0);
-        angle_pass_ptr<1>(reduce4_owner<G>(ga, gl), sn, sd, xs_my, xs_right, gl, cnt, cross_ok, tol2, zero_thr,
+        angle_pass_ptr<G, 1>(reduce4_owner<G>(ga, gl), sn, sd, xs_my, xs_right, gl, cnt, cross_ok, tol2, zero_thr,
                           worst, nrot, T1, T2);
         if (cross_ok) {
           apply<NF>(r[R - 2], x0, true, T1[3], T2[3]);
@@ -582,23 +580,29 @@ jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, 
   }
 }
 
-template <int NF>
+template <int G, int NF>
 static int launch_cluster(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims,
                           float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                           int dim_hi, int* rot_out) {
-  constexpr int G = 16, GPC_MAX = 12;                     // 192 threads: up to 255 registers each
+  constexpr int GPC_MAX = 192 / G;                        // 192 threads: up to 255 registers each
   const int cap = (dims && dim_hi < n) ? dim_hi : n;
   const int groups = (cap + R - 1) / R;
+  // 16-lane groups: portable clusters (<= 8 CTAs).  32-lane groups (rows up to 768 floats): 6 groups
+  // per CTA, so 768 rows need the non-portable cluster size 16 (one such cluster per GPC).
+  const int cmax = (G == 32) ? 16 : 8;
   int csize = 1;
-  while (csize < 8 && csize * GPC_MAX < groups) csize <<= 1;
+  while (csize < cmax && csize * GPC_MAX < groups) csize <<= 1;
   if (csize * GPC_MAX < groups) return -100;
   int gpc = (groups + csize - 1) / csize;
-  gpc = (gpc + 1) & ~1;                                   // whole warps
+  if (G == 16) gpc = (gpc + 1) & ~1;                      // whole warps
   const int threads = gpc * G;
   const size_t nslots = gpc + 1;
   const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
-  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_cluster_kernel<NF>,
+  BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_cluster_kernel<G, NF>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  if (csize > 8)
+    BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_cluster_kernel<G, NF>,
+                                   cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(batch * csize);
   cfg.blockDim = dim3(threads);
@@ -611,7 +615,7 @@ static int launch_cluster(float* Gm, int n, int m, int ld, long stride, int batc
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_oe8_cluster_kernel<NF>, Gm, n, m, ld, stride, dims, tol,
+  BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_oe8_cluster_kernel<G, NF>, Gm, n, m, ld, stride, dims, tol,
                                max_sweeps, sweeps_out, dim_lo, dim_hi, rot_out));
   return 0;
 }
@@ -668,19 +672,25 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
 #undef BASD_OE8
 }
 
-// Cluster variant: up to 768 active rows (8 CTAs x 12 groups x 8 rows) and 384 active columns.
+// Cluster variant: up to 768 active rows; up to 384 active columns with 16-lane groups (portable
+// clusters), up to 768 with 32-lane groups (cluster size 16 for more than 384 rows).
 // Returns -100 when the shape does not fit.
 int launch_jacobi_oe8_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                               float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                               int dim_hi, int* rot_out) {
   const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
   const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
-  if (cap_n > 768 || cap_m > 384) return -100;
-#define BASD_OE8C(NF) \
-  return oe8::launch_cluster<NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
-  if (cap_m <= 256) BASD_OE8C(16);
-  if (cap_m <= 320) BASD_OE8C(20);
-  BASD_OE8C(24);
+  if (cap_n > 768 || cap_m > 768) return -100;
+#define BASD_OE8C(GG, NF) \
+  return oe8::launch_cluster<GG, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+  if (cap_m <= 256) BASD_OE8C(16, 16);
+  if (cap_m <= 320) BASD_OE8C(16, 20);
+  if (cap_m <= 384) BASD_OE8C(16, 24);
+  static const bool wide = getenv("BASD_JACOBI_NO_OE8_WIDE") == nullptr;
+  if (!wide) return -100;
+  if (cap_m <= 512) BASD_OE8C(32, 16);
+  if (cap_m <= 640) BASD_OE8C(32, 20);
+  BASD_OE8C(32, 24);
 #undef BASD_OE8C
 }
 
