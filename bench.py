@@ -20,6 +20,9 @@ import types
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+# load every kernel image up front: with lazy loading the first launch of each kernel variant
+# stalls for milliseconds, wherever in the run it happens to fall
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
