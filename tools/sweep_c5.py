@@ -1,6 +1,6 @@
 """C5 microbench sweep (BASELINE.json configs[4]): loss fwd+bwd over token counts, widths, teacher
-depths and batch sizes on one GPU.  For every point: CUDA-event time of the step (3 warm-ups, 3
-timed), samples/s, and -- with --parity -- loss / gradient agreement with the CPU oracle on a
+depths and batch sizes on one GPU.  For every point: CUDA-event time of the step (4 warm-ups, median of 5
+timed steps), samples/s, and -- with --parity -- loss / gradient agreement with the CPU oracle on a
 batch-4 slice of the same distribution.  Prints one JSON line per point.
 Usage: python tools/sweep_c5.py [--parity] [--quick]"""
 import json, os, sys, time
@@ -34,16 +34,18 @@ def time_point(work):
         loss.backward()
         return loss
 
-    for _ in range(3):
+    for _ in range(4):
         step()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(3):
+    times = []
+    for _ in range(5):                      # per-step events, median: one allocator / host hiccup
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()                           # does not move the reported number
         loss = step()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 3
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = sorted(times)[len(times) // 2]
     return ms, float(loss.detach()), torch.cuda.max_memory_allocated() / 2 ** 30
 
 
