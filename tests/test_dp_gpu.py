@@ -14,7 +14,7 @@ def test_two_rank_loss_equals_concatenated_batch():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tools", "dp_parity.py")]
+           "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tests", "tools", "dp_parity.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(res.stdout[-3000:], res.stderr[-2000:])
     assert res.returncode == 0

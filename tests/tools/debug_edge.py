@@ -1,9 +1,9 @@
 """GPU-box debugging aid for the edge-case workloads of tests/test_edge_cases_gpu.py:
 stage-by-stage distance of the CUDA path from the CPU kernel model."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests.test_edge_cases_gpu import _work
-from tools import debug_stages as ds
+from tests.tools import debug_stages as ds
 
 CASES = {
     "nocls_down": (dict(n_student=196, n_teacher=256, d_student=192, d_teacher=384, has_cls=False,

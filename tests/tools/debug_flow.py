@@ -1,6 +1,6 @@
 """Replicates the pytest flow outside pytest: oracle first, then CUDA, compared with the model."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import basd_b200.synthetic as syn
 from oracle import kernel_model as km

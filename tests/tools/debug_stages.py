@@ -1,7 +1,7 @@
 """GPU-box debugging aid: runs the CUDA phases one by one and prints how far each
 intermediate is from the CPU kernel model (oracle/kernel_model.py)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import basd_b200.synthetic as syn
 from basd_b200 import _engine as eng

@@ -3,7 +3,7 @@ concatenated batch.  python -m torch.distributed.run --nproc-per-node 2 tools/dp
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 

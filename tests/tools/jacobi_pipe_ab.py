@@ -1,6 +1,6 @@
 """Capture the Procrustes X^T matrices of a real step and A/B the two Jacobi paths on them."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import basd_b200.synthetic as syn
 from basd_b200 import _engine as eng

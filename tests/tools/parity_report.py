@@ -1,7 +1,7 @@
 """GPU-box aid: margins of the CUDA path against the live CPU oracle on the parity workloads
 (loss rel. error, max mixing-weight error, min gradient cosine, Procrustes sweeps)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import basd_b200.synthetic as syn
 from tests import _cases as cs

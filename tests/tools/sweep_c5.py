@@ -2,9 +2,9 @@
 depths and batch sizes on one GPU.  For every point: CUDA-event time of the step (4 warm-ups, median of 5
 timed steps), samples/s, and -- with --parity -- loss / gradient agreement with the CPU oracle on a
 batch-4 slice of the same distribution.  Prints one JSON line per point.
-Usage: python tools/sweep_c5.py [--parity] [--quick]"""
+Usage: python tests/tools/sweep_c5.py [--parity] [--quick]"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import basd_b200.synthetic as syn
 from tests import _cases as cs

@@ -34,7 +34,7 @@ SHARD_WAVE_CTAS = int(_os.environ.get("BASD_SHARD_WAVE_CTAS", 148))
 ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerically zero in fp32
 PROC_SV_FLOOR = 2.5e-4   # Procrustes with a Gram side: below sqrt(eps) * sigma_max the recovered v_j is noise
 # both sides direct (no Gram): q_j = normalise(G p_j) is recovered with noise ~eps*sqrt(K)*sigma_max/sigma_j;
-# measured on B200 (tools/debug_edge.py n256): 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
+# measured on B200 (tests/tools/debug_edge.py n256): 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
 MIXED_DIRECT_RATIO = float(_os.environ.get("BASD_MIXED_DIRECT_RATIO", 2.0))
 PROC_SV_FLOOR_DIRECT = float(_os.environ.get("BASD_DIRECT_FLOOR", 3e-5))
 
