@@ -37,6 +37,9 @@ PROC_SV_FLOOR = 2.5e-4   # Procrustes with a Gram side: below sqrt(eps) * sigma_
 # measured on B200 (tests/tools/debug_edge.py n256): 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
 MIXED_DIRECT_RATIO = float(_os.environ.get("BASD_MIXED_DIRECT_RATIO", 2.0))
 PROC_SV_FLOOR_DIRECT = float(_os.environ.get("BASD_DIRECT_FLOOR", 3e-5))
+# Equal factor widths (both sides Gram factors): which side's factor indexes the Jacobi rows.
+# "narrow" = the side with the smaller token dimension (see procrustes_forward), "teacher" = old rule.
+PROC_TIE_Q = _os.environ.get("BASD_PROC_TIE_Q", "narrow")
 
 
 def _f32(*shape, device):
@@ -443,8 +446,17 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
     side_s = _Side(a.view(p, n, d_s), n, direct_s)
     side_t = _Side(bm.view(p, n, d_t), n, direct_t)
     # q = the side with fewer factor columns: the Jacobi sweep orthogonalises the r_q rows of
-    # G = F_q^T F_p (length r_p >= r_q).  Ties keep q = teacher.
+    # G = F_q^T F_p (length r_p >= r_q).  With equal widths (two Gram factors) the sweep implicitly
+    # diagonalises G G^T = L_q^T K_p L_q: the closer K_p is to a multiple of the identity, the closer
+    # this is to L_q^T L_q, one LR step of K_q and already nearly diagonal.  The side with the wider
+    # tokens averages more terms per Gram entry and is the better conditioned one, so it becomes p
+    # (fp32 emulation of the sweep on C2 draws: 10 sweeps / 133k rotations with q = teacher, 7-8
+    # sweeps / 103k with q = student).  A teacher resampled from fewer tokens is rank deficient and
+    # stays q (its zero rows are skipped by the rank-aware sweep).
     swap = side_t.r > side_s.r
+    if (side_t.r == side_s.r and not side_s.direct and not side_t.direct and PROC_TIE_Q == "narrow"
+            and d_s < d_t and n_t >= n):
+        swap = True
     sq, sp = (side_s, side_t) if swap else (side_t, side_s)
     rq, rp = sq.r, sp.r
     g = _f32(p, rq, rp, device=dev)

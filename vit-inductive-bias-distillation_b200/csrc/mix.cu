@@ -10,6 +10,7 @@
 //  basd_weight_grad   : dL/d(mixing weights): inner products of the upstream token gradient
 //                       with every teacher layer, one pass over the stack.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace basd {
 
@@ -49,8 +50,8 @@ __global__ void attn_rows_kernel(const T* __restrict__ attn, int H, int side, in
 }
 
 // One thread per (b, n_dst, 8-wide column group). VEC = 8 elements.
-template <typename TIn, typename TOut, int NE>
-__global__ void __launch_bounds__(256)
+template <typename TIn, typename TOut, int NE, int UNR>
+__global__ void __launch_bounds__(256, (NE <= 4 ? 2 : 1))
 mix_interp_kernel(LayerPtrs layers, int L, int E, const float* __restrict__ weights, int B,
                   int n_src, int n_dst, int D, TOut* __restrict__ out) {
   __shared__ float w[MAX_E * MAX_L];
@@ -74,9 +75,10 @@ mix_interp_kernel(LayerPtrs layers, int L, int E, const float* __restrict__ weig
     for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
   const long off_lo = ((long)b * n_src + lo) * D + g * 8;
   const long off_hi = ((long)b * n_src + hi) * D + g * 8;
-  // layers are walked four at a time with every 128-bit load of the group issued before any
-  // of them is consumed: 4-8 independent requests in flight per thread (HBM latency hiding)
-  constexpr int UNR = 4;
+  // layers are walked UNR (4 or 6) at a time with every 128-bit load of the group issued before
+  // any of them is consumed.  Two 256-thread CTAs fit per SM at <= 128 registers, so the bytes in
+  // flight per SM are 16 warps x 32 lanes x UNR x 16 B: 32 KB at UNR = 4, 48 KB at UNR = 6 --
+  // Little's law at 6.5 TB/s and ~800 ns asks for ~36 KB per SM.
   for (int l0 = 0; l0 < L; l0 += UNR) {
     float v[UNR][8];
 #pragma unroll
@@ -302,8 +304,16 @@ extern "C" int basd_mix_interp(const void* const* teacher_layers, int L, int E, 
   if (int rc = fill_layers(lp, teacher_layers, L)) return rc;
   const long total = (long)B * n_dst * (D >> 3);
   const unsigned grid = (unsigned)((total + 255) / 256);
-#define BASD_MIX(TI, TO, NE) \
-  mix_interp_kernel<TI, TO, NE><<<grid, 256, 0, ST>>>(lp, L, E, weights, B, n_src, n_dst, D, (TO*)out)
+  // six layers in flight when that divides the stack (12, 18, 24 layers), four otherwise
+  static const int unr_env = getenv("BASD_MIX_UNR") ? atoi(getenv("BASD_MIX_UNR")) : 0;
+  const bool six = unr_env ? (unr_env == 6) : (L % 6 == 0);
+#define BASD_MIX(TI, TO, NE)                                                                      \
+  do {                                                                                            \
+    if (six)                                                                                      \
+      mix_interp_kernel<TI, TO, NE, 6><<<grid, 256, 0, ST>>>(lp, L, E, weights, B, n_src, n_dst, D, (TO*)out); \
+    else                                                                                          \
+      mix_interp_kernel<TI, TO, NE, 4><<<grid, 256, 0, ST>>>(lp, L, E, weights, B, n_src, n_dst, D, (TO*)out); \
+  } while (0)
 #define BASD_MIX_E(TI, TO)              \
   do {                                  \
     if (E <= 1) BASD_MIX(TI, TO, 1);    \
