@@ -93,6 +93,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(mhz)}
 
 
+def make_inputs(args, work, seed, device):
+    """Synthetic step inputs.  "backbone": random images through random-init DeiT/ViT/ResNet-50
+    backbones, tokens and attention captured as the reference's trainer does
+    (basd_b200/backbone_features.py).  "spectral": hand-made token spectra (basd_b200/synthetic.py)."""
+    if args.features == "backbone":
+        from basd_b200 import backbone_features as bf
+        out = bf.workload_inputs(args.workload, work, seed=seed, device=device)
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()                      # the backbones' activations are not part of the step
+        return out
+    return syn.make_inputs_fast(work, seed=seed, device=device)
+
+
+def data_label(args):
+    return ("synthetic (random images through random-init backbones)" if args.features == "backbone"
+            else "synthetic (hand-made token spectra)")
+
+
 def build_module(work, device, impl="b200"):
     crit = torch.nn.CrossEntropyLoss(label_smoothing=1.0 / work.num_classes)
     cfg = types.SimpleNamespace(num_extraction_points=work.num_points)
@@ -197,7 +216,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     work = syn.scaled(syn.WORKLOADS[args.workload], args.batch)
     mod = build_module(work, device)
-    logits, targets, st, te, at = syn.make_inputs_fast(work, seed=rank, device=device)
+    logits, targets, st, te, at = make_inputs(args, work, rank, device)
     st = {k: v.requires_grad_(True) for k, v in st.items()}
     logits.requires_grad_(True)
     args5 = (logits, targets, st, te, at)
@@ -327,11 +346,12 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data_label(args),
         "config": {"workload": work.name, "batch_per_gpu": work.batch, "student_tokens": work.n_student,
                    "teacher_tokens": work.n_teacher, "student_dim": work.d_student,
                    "teacher_dim": work.d_teacher, "teacher_layers": work.teacher_layers,
                    "token_dtype": str(work.token_dtype).replace("torch.", ""),
+                   "features": args.features,
                    "cache": "inputs (>=1 GB tokens + attention maps per step) exceed the 126 MB L2",
                    "parallelism": f"dp{world}"},
         "step_ms": [round(x, 2) for x in per_step],
@@ -363,7 +383,7 @@ def cpu_baseline(args, sample_batch, steps):
     torch.set_num_threads(os.cpu_count())
     work = syn.scaled(syn.WORKLOADS[args.workload], sample_batch)
     mod = build_module(work, "cpu", impl="reference")
-    logits, targets, st, te, at = syn.make_inputs_fast(work, seed=0, device="cpu")
+    logits, targets, st, te, at = make_inputs(args, work, 0, "cpu")
     st = {k: v.float().requires_grad_(True) for k, v in st.items()}
     te = {k: v.float() for k, v in te.items()}
     logits.requires_grad_(True)
@@ -387,7 +407,7 @@ def run_reference(args):
     torch.set_num_threads(os.cpu_count())
     work = syn.scaled(syn.WORKLOADS[args.workload], args.cpu_batch)
     mod = build_module(work, "cpu", impl="reference")
-    logits, targets, st, te, at = syn.make_inputs_fast(work, seed=0, device="cpu")
+    logits, targets, st, te, at = make_inputs(args, work, 0, "cpu")
     st = {k: v.float().requires_grad_(True) for k, v in st.items()}
     te = {k: v.float() for k, v in te.items()}
     logits.requires_grad_(True)
@@ -411,11 +431,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT,
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
         "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": data_label(args),
         "config": {"workload": full.name, "batch_per_gpu": full.batch, "student_tokens": full.n_student,
                    "teacher_tokens": full.n_teacher, "student_dim": full.d_student,
                    "teacher_dim": full.d_teacher, "teacher_layers": full.teacher_layers,
                    "token_dtype": "float32 (bf16 tokens upcast: the reference cannot take bf16)",
+                   "features": args.features,
                    "parallelism": "cpu"},
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{steps} step(s) at batch {args.cpu_batch} of the workload's {args.batch} "
@@ -435,6 +456,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--features", default="backbone", choices=["backbone", "spectral"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
