@@ -194,7 +194,7 @@ def pivoted_cholesky(k: torch.Tensor, rel_tol: float = 1e-5):
     return low
 
 
-def procrustes_sample(s_tok, t_tok, w, *, sv_floor: float = 2.5e-4, rel_tol: float = 1e-5,
+def procrustes_sample(s_tok, t_tok, w, *, sv_floor: float = 1e-5, rel_tol: float = 1e-5,
                       direct_sv_floor: float = 1e-5):
     """One sample. s_tok (N,Ds), t_tok (N,Dt) fp32, w (N,) normalised.
     Returns value f = tr_s + tr_t - 2 nuc and the closed-form pieces of its gradient.

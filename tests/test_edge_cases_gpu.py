@@ -115,3 +115,34 @@ def test_importance_rows_instead_of_attention_maps():
     for variant in (rows, cls_only):
         got = cs.run_cuda(work, (logits, targets, st, te, variant), None)
         assert abs(float(got["loss"]) - float(full["loss"])) < 1e-5 * abs(float(full["loss"]))
+
+
+@pytest.mark.parametrize("scale,decay,cos_tol", [(10, 1, 0.9999), (50, 2, 0.9999), (100, 3, 0.9995)])
+def test_ill_conditioned_per_sample_tokens(scale, decay, cos_tol):
+    """Per-sample token matrices with condition numbers 1e2 .. 2e4 (a geometric feature spectrum
+    plus two "massive activation" columns, as trained ViTs show) through the Gram-side Procrustes:
+    the factors square the condition number, so this pins the floor / rank-cut choices
+    (2.5e-4 as the singular-value floor gave cosine 0.9991 at scale 50; tests/tools/floor_sweep.py)."""
+    from basd_b200.losses import geometric_relational_loss
+    from oracle import ref_port as rp
+    gen = torch.Generator().manual_seed(17)
+
+    def tokens(d):
+        q, _ = torch.linalg.qr(torch.randn(d, d, generator=gen))
+        y = (torch.randn(4, 196, d, generator=gen) @ q) * torch.logspace(0, -decay, d)
+        y[..., 7] *= scale
+        y[..., 100] *= scale
+        return y + 0.3 * torch.randn(1, 1, d, generator=gen)
+
+    s, t = tokens(384), tokens(768)
+    attn = torch.softmax(torch.randn(4, 6, 197, 197, generator=gen), dim=-1)
+    sg = s.clone().requires_grad_(True)
+    ref = rp.procrustes_loss(sg, t, attn, True)
+    ref.backward()
+    sd = s.cuda().requires_grad_(True)
+    got = geometric_relational_loss(sd, t.cuda(), attn.cuda(), has_cls_token=True)
+    got.backward()
+    cos = cs.cosine(sd.grad.cpu(), sg.grad)
+    print("ill-conditioned", scale, decay, "loss", float(got), float(ref), "cosine", cos)
+    assert abs(float(got) - float(ref)) / abs(float(ref)) < 1e-3
+    assert cos > cos_tol

@@ -32,7 +32,12 @@ SV_FLOOR = 1e-6          # k x k principal-angle SVD: directions below this are 
 SHARD_SELECTOR_EIG = _os.environ.get("BASD_NO_SELECTOR_SHARDING") is None
 SHARD_WAVE_CTAS = int(_os.environ.get("BASD_SHARD_WAVE_CTAS", 148))
 ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerically zero in fp32
-PROC_SV_FLOOR = 2.5e-4   # Procrustes with a Gram side: below sqrt(eps) * sigma_max the recovered v_j is noise
+# Procrustes with a Gram side: singular directions of G = F_q^T F_p below this fraction of sigma_max
+# leave the polar factor.  The factors are already cut at sqrt(CHOL_TOL) = 3e-3 of their own largest
+# direction, so G's spectrum ends near 1e-5 by itself.  2.5e-4 (the first choice) dropped directions the
+# reference keeps: per-sample tokens with condition number 2e3 gave gradient cosine 0.99909, 0.99999
+# at 1e-5, with every well-conditioned case unchanged (tests/tools/floor_sweep.py, measured on B200).
+PROC_SV_FLOOR = float(_os.environ.get("BASD_PROC_SV_FLOOR", 1e-5))
 # both sides direct (no Gram): q_j = normalise(G p_j) is recovered with noise ~eps*sqrt(K)*sigma_max/sigma_j;
 # measured on B200 (tests/tools/debug_edge.py n256): 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
 MIXED_DIRECT_RATIO = float(_os.environ.get("BASD_MIXED_DIRECT_RATIO", 2.0))
