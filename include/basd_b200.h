@@ -97,6 +97,18 @@ int basd_rowdot(const float* A, int lda, long stride_a, const float* B, int ldb,
 int basd_center_gram(const float* G, const float* colsum, int D, float inv_rows, float* K,
                      int batch, void* stream);
 
+/* Projection of the token-space statistics, computed in double precision (rotate_f64.cu):
+ *   k_centred = fp32( sym(P G P^T) - inv_rows (P c)(P c)^T ),  chat = fp32(P c)
+ * for a batch of (gram (d_in x d_in), colsum (d_in)) pairs sharing the fixed projection
+ * proj (d_out x d_in).  Replaces `student_tokens @ proj_s.T` / `teacher_tokens @ proj_t.T`
+ * (layer_selector.py:72,88) followed by the centring of :35,:91, in Gram form; fp64 because the
+ * rotation of a spectrum spanning cond(X)^2 in fp32 is what limits the selector's gradient.
+ * workspace: basd_rotate_stats_f64_workspace_bytes(...) bytes, 8-byte aligned. */
+long basd_rotate_stats_f64_workspace_bytes(int d_out, int d_in, int batch);
+int basd_rotate_stats_f64(const float* proj, int d_out, int d_in, const float* gram,
+                          const float* colsum, int batch, double inv_rows, void* workspace,
+                          float* k_centred, float* chat, void* stream);
+
 /* Device-side marchenko_pastur_rank (layer_selector.py:8-20) + the cap of :74.
  * lam: (layers, D) spectrum of the uncentred second moment, any order.
  * edges (optional): (layers, 2) = median, lambda_plus. No host sync. */
@@ -190,11 +202,12 @@ int basd_extract_diag(const float* K, int N, int ld, long stride, int batch, flo
 /* rows2 (rq x rq): row j = sigma_j q_j^T, Pt (rq x rp): unit rows p_j^T.  sig = row norms of
  * rows2, nuc = their sum, keep_j = sig_j > rel_floor * max; rows2_j <- keep q_j^T sig^(eq/2),
  * Pt_j <- keep p_j^T sig^(ep/2), pic_j = keep sig^(-(eq+ep)/2); eq, ep in {-1,0,1}.
+ * The derived q_j rows additionally need sig_j > rel_floor_q * max (>= rel_floor).
  * (the singular values / vectors torch.linalg.matrix_norm(ord="nuc") differentiates through,
  * relational.py:48) */
 int basd_procrustes_rows_finish(float* rows2, int rq, int ldr, long stride_r, float* Pt, int rp,
-                                int ldp, long stride_p, int batch, float rel_floor, int eq, int ep,
-                                float* sig, float* nuc, float* pic, void* stream);
+                                int ldp, long stride_p, int batch, float rel_floor, float rel_floor_q,
+                                int eq, int ep, float* sig, float* nuc, float* pic, void* stream);
 /* f = tr_s + tr_t - 2 nuc, gw = df/dw~ from the images IA, IB (rq x N); a non-null Y (N x N,
  * Gram side) becomes 2 diag(sqrt w)(I - Y) in place.                   (relational.py:34-50) */
 int basd_procrustes_grad_prep(float* YA, float* YB, const float* IA, const float* IB, int N, int rq,

@@ -30,8 +30,16 @@ def token_stats(tokens: torch.Tensor):
 
 
 def rotate_stats(gram, colsum, proj):
-    """P G P^T and P c (kernels: sgemm)  -- reference: layer_selector.py:72,88."""
-    return proj @ gram @ proj.T, proj @ colsum
+    """P G P^T and P c in double precision (kernel: basd_rotate_stats_f64) -- reference:
+    layer_selector.py:72,88.  The fp32 version of this product is what limited the selector's
+    gradient on ill-conditioned tokens (cosine 0.9989 -> 0.99999 at condition number 2e3)."""
+    p64 = proj.double()
+    return p64 @ gram.double() @ p64.T, p64 @ colsum.double()
+
+
+def centred(g64, c64, rows):
+    """fp32( sym(P G P^T) - (P c)(P c)^T / M ): one rounding per entry, as the kernel does."""
+    return (0.5 * (g64 + g64.T) - torch.outer(c64, c64) / rows).float()
 
 
 def sym_eig_desc(mat: torch.Tensor):
@@ -62,13 +70,13 @@ def selector_model(student_stats, teacher_stats, rows_s, rows_t, proj_s, proj_t,
         g, c = rotate_stats(gram, col, proj_t)
         lam_u, _ = sym_eig_desc(g)
         k = mp_rank_from_spectrum(lam_u, rows_t, d_s - 1)
-        lam, vec = sym_eig_desc(g - torch.outer(c, c) / rows_t)
+        lam, vec = sym_eig_desc(centred(g, c, rows_t))
         teach.append(dict(k=k, basis=vec[:, :k], sw=lam[:k].clamp(min=0).sqrt()))
     temps = torch.nn.functional.softplus(log_temps)
     out = dict(ranks=[t["k"] for t in teach], dist=[], weights=[], saved=[])
     for i, (gram, col) in enumerate(student_stats):
         g, c = rotate_stats(gram, col, proj_s)
-        lam, vec = sym_eig_desc(g - torch.outer(c, c) / rows_s)
+        lam, vec = sym_eig_desc(centred(g, c, rows_s))
         dist = torch.zeros(len(teach))
         per = []
         for j, t in enumerate(teach):

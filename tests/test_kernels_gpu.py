@@ -324,3 +324,32 @@ def test_mp_rank_secular_matches_direct_spectrum():
         med = spec.flip(0)[(n - 1) // 2]
         assert abs(float(edges[i, 0]) - float(med)) / float(med) < 1e-4
         assert int(ranks[i]) == want or edges[i, 2] == 1
+
+
+@pytest.mark.parametrize("d_out,d_in,batch", [(384, 768, 3), (192, 192, 2), (100, 230, 2)])
+def test_rotate_stats_f64_rounds_once(d_out, d_in, batch):
+    """sym(P G P^T) - (P c)(P c)^T / M in double precision: each fp32 output equals the fp64 result
+    rounded once (the fp32 product it replaces is off by ~1e-6 lambda_max on a graded spectrum)."""
+    nat = _nat()
+    torch.manual_seed(1)
+    rows = 5000
+    x = torch.randn(batch, rows, d_in, dtype=torch.float64) * torch.logspace(0, -3, d_in, dtype=torch.float64)
+    x = x + 0.5
+    gram = (x.transpose(1, 2) @ x).float().to(DEV)
+    col = x.sum(dim=1).float().to(DEV)
+    proj = torch.linalg.qr(torch.randn(d_in, d_in, dtype=torch.float64))[0][:d_out].contiguous().float().to(DEV)
+    k = torch.empty(batch, d_out, d_out, device=DEV)
+    chat = torch.empty(batch, d_out, device=DEV)
+    ws = torch.empty(nat.load().basd_rotate_stats_f64_workspace_bytes(d_out, d_in, batch) // 8,
+                     dtype=torch.float64, device=DEV)
+    nat.call("basd_rotate_stats_f64", nat.ptr(proj), d_out, d_in, nat.ptr(gram), nat.ptr(col), batch,
+             1.0 / rows, nat.ptr(ws), nat.ptr(k), nat.ptr(chat), nat.stream())
+    p64 = proj.double()
+    c64 = col.double() @ p64.T
+    g64 = p64 @ gram.double() @ p64.T
+    ref = 0.5 * (g64 + g64.transpose(1, 2)) - c64.unsqueeze(2) * c64.unsqueeze(1) / rows
+    scale = ref.abs().amax(dim=(1, 2), keepdim=True)
+    # one rounding: relative error <= 2^-24 of each entry, plus fp64 summation-order noise
+    assert ((k.double() - ref).abs() <= 6.1e-8 * ref.abs() + 1e-11 * scale).all()
+    assert (k - k.transpose(1, 2)).abs().max() == 0
+    assert ((chat.double() - c64).abs() <= 6.1e-8 * c64.abs() + 1e-11 * c64.abs().max()).all()

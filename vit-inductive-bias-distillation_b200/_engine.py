@@ -38,6 +38,10 @@ ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerica
 # reference keeps: per-sample tokens with condition number 2e3 gave gradient cosine 0.99909, 0.99999
 # at 1e-5, with every well-conditioned case unchanged (tests/tools/floor_sweep.py, measured on B200).
 PROC_SV_FLOOR = float(_os.environ.get("BASD_PROC_SV_FLOOR", 1e-5))
+# ... except for the side whose vectors are derived (q_j = normalise(G p_j), direction error
+# eps sigma_max / sigma_j) when they enter a Gram-side operator sum_j (F_q q_j)(F_q q_j)^T / sigma_j:
+# at 1e-5 the teacher-token gradient of ill-conditioned tokens came out 41x too large (B200)
+PROC_SV_FLOOR_DERIVED = float(_os.environ.get("BASD_PROC_SV_FLOOR_DERIVED", 2.5e-4))
 # both sides direct (no Gram): q_j = normalise(G p_j) is recovered with noise ~eps*sqrt(K)*sigma_max/sigma_j;
 # measured on B200 (tests/tools/debug_edge.py n256): 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
 MIXED_DIRECT_RATIO = float(_os.environ.get("BASD_MIXED_DIRECT_RATIO", 2.0))
@@ -55,6 +59,7 @@ def _f32(*shape, device):
 # the Procrustes products run on the tensor cores (3xTF32, gemm_tc3.cu) unless this is set
 # (A/B measurements and the SIMT-vs-tensor parity test)
 TC_GEMM = _os.environ.get("BASD_NO_TC_GEMM") is None
+ROTATE_F64 = _os.environ.get("BASD_ROTATE_F32") is None    # A/B knob: fp32 projection of the statistics
 
 
 def sgemm(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch=1, alpha=1.0,
@@ -298,26 +303,36 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     l, d_t, _ = stats.gram_t.shape
     # rows < D_s (the reference's M < D branch, layer_selector.py:14-15): the M x M Gram it switches
     # to has the M largest eigenvalues of the D_s x D_s one; the MP kernels take the median over those
-    # --- rotate the token-space statistics by the fixed projections (exact in fp32)
-    tmp_t = _f32(l, d_s, d_t, device=dev)
-    sgemm(0, 0, d_s, d_t, d_t, proj_t, d_t, 0, stats.gram_t, d_t, d_t * d_t, tmp_t, d_t, d_s * d_t, l)
-    ghat_t = _f32(l, d_s, d_s, device=dev)
-    sgemm(0, 1, d_s, d_s, d_t, tmp_t, d_t, d_s * d_t, proj_t, d_t, 0, ghat_t, d_s, d_s * d_s, l)
+    # --- rotate the token-space statistics by the fixed projections and centre them
+    kall = _f32(l + e, d_s, d_s, device=dev)
     chat_t = _f32(l, d_s, device=dev)
-    sgemm(0, 1, l, d_s, d_t, stats.col_t, d_t, 0, proj_t, d_t, 0, chat_t, d_s, 0, 1)
-    tmp_s = _f32(e, d_s, d_s, device=dev)
-    sgemm(0, 0, d_s, d_s, d_s, proj_s, d_s, 0, stats.gram_s, d_s, d_s * d_s, tmp_s, d_s, d_s * d_s, e)
-    ghat_s = _f32(e, d_s, d_s, device=dev)
-    sgemm(0, 1, d_s, d_s, d_s, tmp_s, d_s, d_s * d_s, proj_s, d_s, 0, ghat_s, d_s, d_s * d_s, e)
     chat_s = _f32(e, d_s, device=dev)
-    sgemm(0, 1, e, d_s, d_s, stats.col_s, d_s, 0, proj_s, d_s, 0, chat_s, d_s, 0, 1)
-
+    if ROTATE_F64:
+        # fp64 products, one rounding per entry of K (rotate_f64.cu): the fp32 rotation of a spectrum
+        # spanning cond(X)^2 is what limits the selector's gradient on ill-conditioned tokens
+        for proj, gram, col, rows, k_out, c_out in ((proj_t, stats.gram_t, stats.col_t, rows_t, kall[:l], chat_t),
+                                                    (proj_s, stats.gram_s, stats.col_s, rows_s, kall[l:], chat_s)):
+            nb, d_in = gram.shape[0], gram.shape[1]
+            ws = torch.empty(nat.load().basd_rotate_stats_f64_workspace_bytes(d_s, d_in, nb) // 8,
+                             dtype=torch.float64, device=dev)
+            call("basd_rotate_stats_f64", ptr(proj), d_s, d_in, ptr(gram), ptr(col), nb, 1.0 / rows,
+                 ptr(ws), ptr(k_out), ptr(c_out), stream())
+    else:
+        tmp_t = _f32(l, d_s, d_t, device=dev)
+        sgemm(0, 0, d_s, d_t, d_t, proj_t, d_t, 0, stats.gram_t, d_t, d_t * d_t, tmp_t, d_t, d_s * d_t, l)
+        ghat_t = _f32(l, d_s, d_s, device=dev)
+        sgemm(0, 1, d_s, d_s, d_t, tmp_t, d_t, d_s * d_t, proj_t, d_t, 0, ghat_t, d_s, d_s * d_s, l)
+        sgemm(0, 1, l, d_s, d_t, stats.col_t, d_t, 0, proj_t, d_t, 0, chat_t, d_s, 0, 1)
+        tmp_s = _f32(e, d_s, d_s, device=dev)
+        sgemm(0, 0, d_s, d_s, d_s, proj_s, d_s, 0, stats.gram_s, d_s, d_s * d_s, tmp_s, d_s, d_s * d_s, e)
+        ghat_s = _f32(e, d_s, d_s, device=dev)
+        sgemm(0, 1, d_s, d_s, d_s, tmp_s, d_s, d_s * d_s, proj_s, d_s, 0, ghat_s, d_s, d_s * d_s, e)
+        sgemm(0, 1, e, d_s, d_s, stats.col_s, d_s, 0, proj_s, d_s, 0, chat_s, d_s, 0, 1)
+        call("basd_center_gram", ptr(ghat_t), ptr(chat_t), d_s, 1.0 / rows_t, ptr(kall[:l]), l, stream())
+        call("basd_center_gram", ptr(ghat_s), ptr(chat_s), d_s, 1.0 / rows_s, ptr(kall[l:]), e, stream())
     # --- [centred teacher | centred student] eigenproblems in one batch.  The uncentred teacher
     # spectrum (only needed for the MP rank) follows from the centred one by the rank-one
     # secular equation, so it costs no eigenproblem of its own.
-    kall = _f32(l + e, d_s, d_s, device=dev)
-    call("basd_center_gram", ptr(ghat_t), ptr(chat_t), d_s, 1.0 / rows_t, ptr(kall[:l]), l, stream())
-    call("basd_center_gram", ptr(ghat_s), ptr(chat_s), d_s, 1.0 / rows_s, ptr(kall[l:]), e, stream())
     lam, vt = sharded_sym_eig(kall, group, world)
     lam_t, lam_s = lam[:l], lam[l:]
     vt_t, vt_s = vt[:l], vt[l:]
@@ -487,11 +502,14 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
         e_s = 1
     eq, ep = (e_s, e_t) if swap else (e_t, e_s)
     floor = PROC_SV_FLOOR_DIRECT if (side_s.direct and side_t.direct) else PROC_SV_FLOOR
+    # the q vectors are derived (normalised rows of P^T G^T); the Gram-side operator they enter
+    # (Y_p, the p side's gradient) divides by sigma and takes the higher floor
+    floor_q = floor if sp.direct else max(floor, PROC_SV_FLOOR_DERIVED)
     sig = _f32(p, rq, device=dev)
     pic = _f32(p, rq, device=dev)
     nuc = _f32(p, device=dev)
     call("basd_procrustes_rows_finish", ptr(rows2), rq, rq, rq * rq, ptr(pt), rp, rp, rq * rp, p,
-         floor, eq, ep, ptr(sig), ptr(nuc), ptr(pic), stream())
+         floor, floor_q, eq, ep, ptr(sig), ptr(nuc), ptr(pic), stream())
     f = _f32(p, device=dev)
     m_a = m_b = g_a = g_b = gw = None
     if with_grad:

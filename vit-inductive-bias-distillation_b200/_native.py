@@ -31,6 +31,8 @@ _SIG = {
     "basd_rows_normalize": [_p, _i, _i, _i, _l, _p, _i, _l, _p, _i, _i, _i, _f, _p, _p],
     "basd_rowdot": [_p, _i, _l, _p, _i, _l, _i, _i, _i, _p, _p],
     "basd_center_gram": [_p, _p, _i, _f, _p, _i, _p],
+    "basd_rotate_stats_f64_workspace_bytes": [_i, _i, _i],
+    "basd_rotate_stats_f64": [_p, _i, _i, _p, _p, _i, C.c_double, _p, _p, _p, _p],
     "basd_mp_rank": [_p, _i, _l, _i, _p, _p, _i, _p],
     "basd_mp_rank_secular": [_p, _p, _i, _l, _i, _p, _p, _i, _p],
     "basd_expand_ranks": [_p, _i, _i, _p, _p],
@@ -48,7 +50,7 @@ _SIG = {
     "basd_weight_grad": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],
     "basd_weighted_center": [_p, _i, _l, _p, _l, _i, _i, _p, _l, _i, _p],
     "basd_extract_diag": [_p, _i, _i, _l, _i, _p, _p],
-    "basd_procrustes_rows_finish": [_p, _i, _i, _l, _p, _i, _i, _l, _i, _f, _i, _i, _p, _p, _p, _p],
+    "basd_procrustes_rows_finish": [_p, _i, _i, _l, _p, _i, _i, _l, _i, _f, _f, _i, _i, _p, _p, _p, _p],
     "basd_procrustes_grad_prep": [_p, _p, _p, _p, _i, _i, _i, _l, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p,
                                   _p, _i, _p],
     "basd_procrustes_direct_grad": [_p, _p, _p, _i, _i, _i, _p],
@@ -60,7 +62,7 @@ _SIG = {
                                  _p, _p],
     "basd_cast_out": [_p, _p, _i, _l, _p],
 }
-_RET = {"basd_token_gram_simt_workspace_floats": _l}
+_RET = {"basd_token_gram_simt_workspace_floats": _l, "basd_rotate_stats_f64_workspace_bytes": _l}
 # optional symbols (present once the tcgen05 Gram is built)
 _OPTIONAL = {
     "basd_token_gram_tc_workspace_bytes": ([_l, _i], _l),

@@ -126,9 +126,14 @@ __global__ void extract_diag_kernel(const float* __restrict__ K, int N, int ld, 
 // rows2 (rq x rq) = P^T X: row j = sigma_j q_j^T;  Pt (rq x rp): row j = p_j^T (unit).
 // Produces per sample:
 //   sig[j] = |rows2_j| (refined singular values), nuc = sum_j sig[j], keep_j = sig_j > rel_floor * max(sig)
-//   rows2[j,:] <- keep_j * q_j^T * sig_j^(eq/2)        Pt[j,:] <- keep_j * p_j^T * sig_j^(ep/2)
+//   rows2[j,:] <- keepq_j * q_j^T * sig_j^(eq/2)       Pt[j,:] <- keep_j * p_j^T * sig_j^(ep/2)
 //   pic[j]      = keep_j * sig_j^(-(eq+ep)/2)          (eq, ep in {-1, 0, +1})
 // so that images I = rows . F^T of the two sides recombine as  sum_j pic_j I_q[j,n] I_p[j,n].
+// keepq_j = sig_j > rel_floor_q * max(sig) with rel_floor_q >= rel_floor: the q_j are DERIVED vectors
+// (normalised rows of P^T G^T, direction error ~ eps sigma_max / sigma_j), while the p_j come out of the
+// Jacobi sweep orthogonal to working precision.  The operator built from the q images,
+// Y_p = sum_j (F_q q_j)(F_q q_j)^T / sigma_j, divides that error by sigma_j once more, so it takes the
+// higher floor; the one built from the p images keeps every direction above rel_floor.
 __device__ __forceinline__ float half_power(float sg, int e2) {
   return e2 == 0 ? 1.f : (e2 < 0 ? rsqrtf(sg) : sqrtf(sg));
 }
@@ -136,8 +141,9 @@ __device__ __forceinline__ float half_power(float sg, int e2) {
 __global__ void __launch_bounds__(512)
 procrustes_rows_finish_kernel(float* __restrict__ rows2, int rq, int ldr, long stride_r,
                               float* __restrict__ Pt, int rp, int ldp, long stride_p,
-                              float rel_floor, int eq, int ep, float* __restrict__ sig,
-                              float* __restrict__ nuc, float* __restrict__ pic) {
+                              float rel_floor, float rel_floor_q, int eq, int ep,
+                              float* __restrict__ sig, float* __restrict__ nuc,
+                              float* __restrict__ pic) {
   extern __shared__ float sm[];
   float* nrm = sm;        // rq
   float* red = sm + rq;   // 32
@@ -157,10 +163,12 @@ procrustes_rows_finish_kernel(float* __restrict__ rows2, int rq, int ldr, long s
   mx = block_max(mx, red);
   tot = block_sum(tot, red);
   const float floor_v = rel_floor * mx;
+  const float floor_q = fmaxf(rel_floor, rel_floor_q) * mx;
   for (int r = warp; r < rq; r += nw) {
     const float sg = nrm[r];
     const bool keep = sg > floor_v && sg > 0.f;
-    const float fq = keep ? half_power(sg, eq) / sg : 0.f;     // rows2_j / sig_j = q_j^T
+    const bool keepq = keep && sg > floor_q;
+    const float fq = keepq ? half_power(sg, eq) / sg : 0.f;    // rows2_j / sig_j = q_j^T
     const float fp = keep ? half_power(sg, ep) : 0.f;
     for (int c = lane; c < rq; c += 32) R[(long)r * ldr + c] *= fq;
     for (int c = lane; c < rp; c += 32) U[(long)r * ldp + c] *= fp;
@@ -338,12 +346,12 @@ extern "C" int basd_extract_diag(const float* K, int N, int ld, long stride, int
 
 extern "C" int basd_procrustes_rows_finish(float* rows2, int rq, int ldr, long stride_r, float* Pt,
                                            int rp, int ldp, long stride_p, int batch,
-                                           float rel_floor, int eq, int ep, float* sig, float* nuc,
-                                           float* pic, void* stream) {
+                                           float rel_floor, float rel_floor_q, int eq, int ep,
+                                           float* sig, float* nuc, float* pic, void* stream) {
   if (batch <= 0) return 0;
   if (eq < -1 || eq > 1 || ep < -1 || ep > 1) return -2;
   procrustes_rows_finish_kernel<<<batch, 512, (rq + 32) * sizeof(float), ST>>>(
-      rows2, rq, ldr, stride_r, Pt, rp, ldp, stride_p, rel_floor, eq, ep, sig, nuc, pic);
+      rows2, rq, ldr, stride_r, Pt, rp, ldp, stride_p, rel_floor, rel_floor_q, eq, ep, sig, nuc, pic);
   BASD_LAUNCH_CHECK();
   return 0;
 }
