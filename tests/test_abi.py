@@ -59,3 +59,36 @@ def test_cpu_tensors_are_rejected():
         assert "CUDA" in str(e) or "CPU" in str(e)
     else:
         raise AssertionError("CPU tensors must not silently run")
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/basd_b200.h is consumed as C (not C++) and a C program links against the library:
+    the host-only sizing entry points answer without a GPU (what a cgo / JNI / plain-C binding
+    would call first)."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as entry
+    entry.build()
+    from basd_b200 import _native as nat
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "basd_b200.h")], check=True)
+    src = tmp_path / "probe.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "basd_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%d %ld %d\\n", basd_weight_grad_slices(),\n'
+        "         basd_token_gram_tc_workspace_bytes(50176L, 768),\n"
+        "         basd_gemm_tc3_supported(196, 196, 196, 196, 196, 196, 38416L, 38416L, 38416L));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "probe"
+    libdir = os.path.dirname(nat.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lbasd_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    slices, ws_bytes, ok = int(out[0]), int(out[1]), int(out[2])
+    assert slices > 0 and slices % 148 == 0              # grid sized in multiples of the SM count
+    assert ws_bytes >= 768 * 768 * 4                     # at least one D x D fp32 partial
+    assert ok in (0, 1)
