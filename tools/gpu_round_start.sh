@@ -1,0 +1,39 @@
+#!/usr/bin/env bash
+# One gpurun call that banks the round's baseline evidence before any kernel work:
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round_start.sh r2'
+# Order = value per GPU-minute: bench line, ncu launch list, full captures, then the GPU test suite.
+# On a fresh box the first `import torch` + eager module loading + backbone features take ~2 min,
+# so no step gets less than 300 s (round 1 lost its last launch-list refresh to a 110 s limit).
+set -u
+tag="${1:-rN}"
+out=gpurun_out
+mkdir -p "$out"
+step() { echo "== $1 (limit $2 s)"; shift; }
+
+echo "== bench c2"
+timeout 400 python bench.py --steps 5 --warmup 3 > "$out/${tag}_bench_c2.json" 2> "$out/${tag}_bench_c2.err"
+echo "bench rc $?"
+
+echo "== profiled program without ncu"
+if timeout 400 python tools/profile_step.py c2 256 > "$out/${tag}_profile_step.log" 2>&1; then
+  echo "== ncu launch list"
+  timeout 500 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file "$out/${tag}_launches_c2_b256.csv" python tools/profile_step.py c2 256 > "$out/${tag}_ncu_launches.log" 2>&1
+  echo "launch list rc $?"
+  echo "== ncu --set full, top kernels, batch 64"
+  timeout 300 python tools/profile_step.py c2 64 > "$out/${tag}_profile_step_b64.log" 2>&1 && \
+  timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
+    -k regex:"oe8|gemm_tc3|pivoted_cholesky_left4|token_gram_tc|mix_interp|weight_grad_kernel" -c 24 \
+    -o "$out/${tag}_full_c2_b64" python tools/profile_step.py c2 64 > "$out/${tag}_ncu_full.log" 2>&1
+  echo "full capture rc $?"
+  if [ -f "$out/${tag}_full_c2_b64.ncu-rep" ]; then
+    ncu -i "$out/${tag}_full_c2_b64.ncu-rep" --page raw --csv > "$out/${tag}_full_c2_b64_raw.csv" 2>/dev/null
+  fi
+else
+  echo "profile_step failed or timed out: see $out/${tag}_profile_step.log"
+fi
+
+echo "== pytest -m gpu"
+timeout 1500 python -m pytest tests -m gpu -x -q > "$out/${tag}_pytest_gpu.log" 2>&1
+echo "pytest rc $?"
+tail -5 "$out/${tag}_pytest_gpu.log"
