@@ -8,7 +8,6 @@ set -u
 tag="${1:-rN}"
 out=gpurun_out
 mkdir -p "$out"
-step() { echo "== $1 (limit $2 s)"; shift; }
 
 echo "== bench c2"
 timeout 400 python bench.py --steps 5 --warmup 3 > "$out/${tag}_bench_c2.json" 2> "$out/${tag}_bench_c2.err"
