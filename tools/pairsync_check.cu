@@ -1,0 +1,80 @@
+// Torch-free check of the Jacobi step-synchronisation variants (starts in about a second on a
+// fresh GPU box, where `import torch` alone takes a minute):
+//   build/pairsync_check <out.bin> [batch n m]      run once per mode, the mode comes from the
+//   BASD_JACOBI_PAIRSYNC environment variable; prints ms per launch and the mean sweep count and
+//   writes the orthogonalised rows + sweep counts to <out.bin>;  `cmp` of two outputs = bitwise A/B.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -Iinclude tools/pairsync_check.cu \
+//        -o build/pairsync_check -Lvit-inductive-bias-distillation_b200/lib -lbasd_b200 \
+//        -Xlinker -rpath -Xlinker '$ORIGIN/../vit-inductive-bias-distillation_b200/lib'
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "basd_b200.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); return 2; } } while (0)
+
+int main(int argc, char** argv) {
+  const char* out = argc > 1 ? argv[1] : "/tmp/pairsync.bin";
+  const int batch = argc > 2 ? std::atoi(argv[2]) : 1024;
+  const int n = argc > 3 ? std::atoi(argv[3]) : 196;
+  const int m = argc > 4 ? std::atoi(argv[4]) : 196;
+  const size_t per = (size_t)n * m, total = per * batch;
+  std::vector<float> host(total);
+  // graded rows (like a product of two pivoted-Cholesky factors) plus a dense coupling
+  unsigned long long s = 88172645463325252ull;
+  auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (float)((s >> 11) * (1.0 / 9007199254740992.0)) * 2.f - 1.f; };
+  for (int b = 0; b < batch; ++b)
+    for (int i = 0; i < n; ++i) {
+      const float scale = std::pow(10.f, -3.f * i / n);
+      for (int j = 0; j < m; ++j) host[b * per + (size_t)i * m + j] = scale * (rnd() + (i == j ? 2.f : 0.f));
+    }
+  float *d_in = nullptr, *d_work = nullptr;
+  int* d_sweeps = nullptr;
+  CK(cudaMalloc(&d_in, total * sizeof(float)));
+  CK(cudaMalloc(&d_work, total * sizeof(float)));
+  CK(cudaMalloc(&d_sweeps, batch * sizeof(int)));
+  CK(cudaMemcpy(d_in, host.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaMemcpy(d_work, d_in, total * sizeof(float), cudaMemcpyDeviceToDevice));
+    CK(cudaMemset(d_sweeps, 0, batch * sizeof(int)));
+    CK(cudaEventRecord(e0, 0));
+    const int rc = basd_jacobi_rows(d_work, n, m, m, (long)per, batch, nullptr, 1e-6f, 18, d_sweeps, nullptr);
+    CK(cudaEventRecord(e1, 0));
+    if (rc) { std::fprintf(stderr, "basd_jacobi_rows rc %d\n", rc); return 3; }
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep && ms < best) best = ms;
+  }
+  std::vector<int> sweeps(batch);
+  CK(cudaMemcpy(host.data(), d_work, total * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sweeps.data(), d_sweeps, batch * sizeof(int), cudaMemcpyDeviceToHost));
+  double mean = 0, worst = 0;
+  for (int v : sweeps) mean += v;
+  // orthogonality of the first problem's rows (largest |cos| between rows above 1e-6 of the largest)
+  {
+    std::vector<double> nr(n);
+    double mx = 0;
+    for (int i = 0; i < n; ++i) { double a = 0; for (int j = 0; j < m; ++j) a += (double)host[(size_t)i * m + j] * host[(size_t)i * m + j]; nr[i] = std::sqrt(a); mx = std::fmax(mx, nr[i]); }
+    for (int i = 0; i < n; ++i) for (int k = i + 1; k < n; ++k) {
+      if (nr[i] < 1e-6 * mx || nr[k] < 1e-6 * mx) continue;
+      double d = 0; for (int j = 0; j < m; ++j) d += (double)host[(size_t)i * m + j] * host[(size_t)k * m + j];
+      worst = std::fmax(worst, std::fabs(d) / (nr[i] * nr[k]));
+    }
+  }
+  std::printf("pairsync=%s batch %d n %d m %d: %.3f ms per launch, sweeps mean %.2f, max |cos| %.2e\n",
+              std::getenv("BASD_JACOBI_PAIRSYNC") ? "1" : "0", batch, n, m, best, mean / batch, worst);
+  FILE* f = std::fopen(out, "wb");
+  if (!f) return 4;
+  std::fwrite(host.data(), sizeof(float), total, f);
+  std::fwrite(sweeps.data(), sizeof(int), batch, f);
+  std::fclose(f);
+  return 0;
+}
