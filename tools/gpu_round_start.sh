@@ -32,13 +32,6 @@ else
   echo "profile_step failed or timed out: see $out/${tag}_profile_step.log"
 fi
 
-echo "== Jacobi neighbour-only synchronisation A/B (opt-in variant written at the end of round 1)"
-timeout 600 python tools/pairsync_ab.py > "$out/${tag}_pairsync_ab.log" 2>&1
-echo "pairsync A/B rc $? (0 = bitwise equal)"; tail -8 "$out/${tag}_pairsync_ab.log"
-BASD_JACOBI_PAIRSYNC=1 timeout 600 compute-sanitizer --tool racecheck python tools/pairsync_ab.py child small \
-  > "$out/${tag}_pairsync_racecheck.log" 2>&1
-echo "racecheck rc $?"; tail -3 "$out/${tag}_pairsync_racecheck.log"
-
 echo "== pytest -m gpu"
 timeout 1500 python -m pytest tests -m gpu -x -q > "$out/${tag}_pytest_gpu.log" 2>&1
 echo "pytest rc $?"

@@ -1,10 +1,12 @@
-// Torch-free check of the Jacobi step-synchronisation variants (starts in about a second on a
-// fresh GPU box, where `import torch` alone takes a minute):
-//   build/pairsync_check <out.bin> [batch n m]      run once per mode, the mode comes from the
-//   BASD_JACOBI_PAIRSYNC environment variable; prints ms per launch and the mean sweep count and
-//   writes the orthogonalised rows + sweep counts to <out.bin>;  `cmp` of two outputs = bitwise A/B.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -Iinclude tools/pairsync_check.cu \
-//        -o build/pairsync_check -Lvit-inductive-bias-distillation_b200/lib -lbasd_b200 \
+// Torch-free timing / determinism check of the batched row Jacobi (basd_jacobi_rows) through the C ABI.
+// Starts in about a second on a fresh GPU box, where `import torch` alone takes a minute, so an A/B of
+// two builds or two environment switches fits in a sub-minute GPU call:
+//   build/jacobi_check <out.bin> [batch n m]   prints ms per launch, mean sweep count and the largest
+//   |cos| between the resulting rows, writes rows + sweep counts to <out.bin>; `cmp` two outputs for a
+//   bitwise A/B (the sweep is deterministic).  Used at the end of round 1 for the neighbour-only
+//   synchronisation experiment.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -Iinclude tools/jacobi_check.cu \
+//        -o build/jacobi_check -Lvit-inductive-bias-distillation_b200/lib -lbasd_b200 \
 //        -Xlinker -rpath -Xlinker '$ORIGIN/../vit-inductive-bias-distillation_b200/lib'
 #include <cuda_runtime.h>
 #include <cmath>
@@ -17,7 +19,7 @@
   std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); return 2; } } while (0)
 
 int main(int argc, char** argv) {
-  const char* out = argc > 1 ? argv[1] : "/tmp/pairsync.bin";
+  const char* out = argc > 1 ? argv[1] : "/tmp/jacobi_check.bin";
   const int batch = argc > 2 ? std::atoi(argv[2]) : 1024;
   const int n = argc > 3 ? std::atoi(argv[3]) : 196;
   const int m = argc > 4 ? std::atoi(argv[4]) : 196;
@@ -69,8 +71,8 @@ int main(int argc, char** argv) {
       worst = std::fmax(worst, std::fabs(d) / (nr[i] * nr[k]));
     }
   }
-  std::printf("pairsync=%s batch %d n %d m %d: %.3f ms per launch, sweeps mean %.2f, max |cos| %.2e\n",
-              std::getenv("BASD_JACOBI_PAIRSYNC") ? "1" : "0", batch, n, m, best, mean / batch, worst);
+  std::printf("batch %d n %d m %d: %.3f ms per launch, sweeps mean %.2f, max |cos| %.2e\n", batch, n, m, best,
+              mean / batch, worst);
   FILE* f = std::fopen(out, "wb");
   if (!f) return 4;
   std::fwrite(host.data(), sizeof(float), total, f);

@@ -175,79 +175,20 @@ __device__ __forceinline__ void angle_pass(float g_own, float& sn, float& sd, fl
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Neighbour-only synchronisation (opt-in variant, BASD_JACOBI_PAIRSYNC=1; not yet measured).
-// The two block-wide barriers of a step pair exist for ONE dependency: the position-0 row of a
-// group (shared memory) is touched by the group itself in even steps and by its left neighbour in
-// odd steps.  With two groups per warp that dependency crosses a warp boundary only between warp w
-// and warp w + 1, so each boundary gets two mbarriers (count 1, one elected lane arrives):
-//   A[b]: "warp b finished its even step"  -- warp b arrives, warp b - 1 waits before its odd step
-//   B[b]: "warp b - 1 finished its odd step" -- warp b - 1 arrives, warp b waits before its next even step
-// Every warp uses every barrier of its two boundaries exactly once per step pair, so all waits use
-// one phase bit that toggles per step pair.  Warps may then drift apart by up to one step per
-// boundary: the dot -> reduce -> angle -> rotate latency chain of one warp overlaps the FMA phase
-// of others instead of being exposed at a block-wide barrier.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void pair_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void pair_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "OE8_WAIT:\n"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra OE8_DONE;\n"
-      "bra OE8_WAIT;\n"
-      "OE8_DONE:\n"
-      "}\n" ::"r"(smem_addr(bar)),
-      "r"(parity)
-      : "memory");
-}
-constexpr int MAX_WARPS = 32;
-// after an even step: tell the left warp this warp's position-0 rows are final, wait for the right warp's
-template <bool PAIR>
-__device__ __forceinline__ void sync_after_even(uint64_t* bars, int warp, int nw, int lane, uint32_t ph) {
-  if constexpr (!PAIR) {
-    __syncthreads();
-  } else {
-    __syncwarp();
-    if (warp > 0 && lane == 0) pair_arrive(bars + warp);
-    if (warp + 1 < nw) pair_wait(bars + warp + 1, ph);
-    __syncwarp();
-  }
-}
-// after an odd step: tell the right warp its first position-0 row is released, wait for the left warp
-template <bool PAIR>
-__device__ __forceinline__ void sync_after_odd(uint64_t* bars, int warp, int nw, int lane, uint32_t ph) {
-  if constexpr (!PAIR) {
-    __syncthreads();
-  } else {
-    __syncwarp();
-    if (warp + 1 < nw && lane == 0) pair_arrive(bars + MAX_WARPS + warp + 1);
-    if (warp > 0) pair_wait(bars + MAX_WARPS + warp, ph);
-    __syncwarp();
-  }
-}
-
 // Row state (squared norm, scale) is DISTRIBUTED: lane p (1..7) of a group holds the state of
 // position p, position 0's state lives in shared memory next to its row.  The four angles of a
 // step are computed in ONE pass, each by the lane that owns the pair's left position (instead of
 // four redundant evaluations on all 16 lanes); partner states travel by shuffles (width 16) and
 // the two stored-row multipliers of every pair are broadcast back.
-template <int G, int NF, bool PAIR>    // G lanes per group; NF floats per lane per row: columns lane + G j, j < NF
-__device__ __forceinline__ void
-jacobi_rows_oe8_body(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                     const int* __restrict__ dims, float tol, int max_sweeps,
-                     int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
-                     int* __restrict__ rot_out, int rows_only, uint64_t* pair_bars) {
+template <int G, int NF>    // G lanes per group; NF floats per lane per row: columns lane + G j, j < NF
+__global__ void __launch_bounds__(G == 16 ? 512 : 896, 1)
+jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                       const int* __restrict__ dims, float tol, int max_sweeps,
+                       int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
+                       int* __restrict__ rot_out, int rows_only) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_scratch[32];
   const int prob = blockIdx.x, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31, nw = (blockDim.x + 31) >> 5;
-  uint32_t pair_phase = 0;
   // dims: active leading size of a square problem (rows and columns), or -- rows_only -- the
   // number of leading non-zero rows of a rank-deficient factor product (all columns active)
   if (dims && !rows_only && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;
@@ -364,7 +305,7 @@ jacobi_rows_oe8_body(float* __restrict__ Gbase, int n, int m, int ld, long strid
       }
 #pragma unroll
       for (int k = 1; k < 4; ++k) apply<NF>(r[2 * k - 1], r[2 * k], 2 * k + 1 < cnt, T1[k], T2[k]);
-      sync_after_even<PAIR>(pair_bars, warp, nw, lane, pair_phase);
+      __syncthreads();
       // ---------------- odd step: (1,2) (3,4) (5,6), (7, right neighbour's 0) through shared memory
       if (step + 1 < nn) {
         ga[3] = dot_smem<G, NF>(right_row, r[R - 2]);
@@ -382,8 +323,7 @@ jacobi_rows_oe8_body(float* __restrict__ Gbase, int n, int m, int ld, long strid
 #pragma unroll
         for (int k = 0; k < 3; ++k) apply<NF>(r[2 * k], r[2 * k + 1], 2 * k + 2 < cnt, T1[k], T2[k]);
       }
-      sync_after_odd<PAIR>(pair_bars, warp, nw, lane, pair_phase);
-      pair_phase ^= 1u;
+      __syncthreads();
     }
     worst = block_max(worst, red_scratch);
     if (worst < tol) { ++sweep; break; }
@@ -415,31 +355,6 @@ jacobi_rows_oe8_body(float* __restrict__ Gbase, int n, int m, int ld, long strid
     const float tot = block_sum((float)nrot, red_scratch);
     if (tid == 0) atomicAdd(rot_out + prob, (int)tot);
   }
-}
-
-template <int G, int NF>
-__global__ void __launch_bounds__(G == 16 ? 512 : 896, 1)
-jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                       const int* __restrict__ dims, float tol, int max_sweeps,
-                       int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
-                       int* __restrict__ rot_out, int rows_only) {
-  jacobi_rows_oe8_body<G, NF, false>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo,
-                                     dim_hi, rot_out, rows_only, nullptr);
-}
-
-// Same sweep with the neighbour-only synchronisation described above (opt-in).
-template <int G, int NF>
-__global__ void __launch_bounds__(G == 16 ? 512 : 896, 1)
-jacobi_rows_oe8_pairsync_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                                const int* __restrict__ dims, float tol, int max_sweeps,
-                                int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
-                                int* __restrict__ rot_out, int rows_only) {
-  __shared__ __align__(8) uint64_t pair_bars[2 * MAX_WARPS];
-  if (threadIdx.x < 2 * MAX_WARPS)
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(pair_bars + threadIdx.x)), "r"(1));
-  __syncthreads();
-  jacobi_rows_oe8_body<G, NF, true>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo,
-                                    dim_hi, rot_out, rows_only, pair_bars);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -715,19 +630,6 @@ static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const
   if (threads < 64) threads = 64;
   const size_t nslots = threads / G + 1;
   const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
-  // neighbour-only step synchronisation: written after round 1's GPU budget was spent, so it stays
-  // opt-in until it has been race-checked and timed against the block-wide barriers
-  static const bool pairsync = getenv("BASD_JACOBI_PAIRSYNC") != nullptr;
-  if constexpr (G == 16) {
-    if (pairsync && threads >= 64) {
-      BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_pairsync_kernel<G, NF>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-      jacobi_rows_oe8_pairsync_kernel<G, NF><<<batch, threads, dyn, st>>>(
-          Gm, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi, rot_out, rows_only);
-      BASD_LAUNCH_CHECK();
-      return 0;
-    }
-  }
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_kernel<G, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dyn));
   jacobi_rows_oe8_kernel<G, NF><<<batch, threads, dyn, st>>>(Gm, n, m, ld, stride, dims, tol, max_sweeps,
