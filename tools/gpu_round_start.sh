@@ -9,6 +9,17 @@ tag="${1:-rN}"
 out=gpurun_out
 mkdir -p "$out"
 
+echo "== Jacobi split experiment (torch-free harness, seconds): default vs 2 / 4 CTAs per problem"
+if [ -x build/jacobi_check ]; then
+  timeout 20 build/jacobi_check /tmp/j0.bin > "$out/${tag}_jacobi_split.log" 2>&1
+  BASD_JACOBI_SPLIT=2 timeout 20 build/jacobi_check /tmp/j2.bin >> "$out/${tag}_jacobi_split.log" 2>&1
+  BASD_JACOBI_SPLIT=4 timeout 20 build/jacobi_check /tmp/j4.bin >> "$out/${tag}_jacobi_split.log" 2>&1
+  cmp /tmp/j0.bin /tmp/j2.bin >> "$out/${tag}_jacobi_split.log" 2>&1 && echo "split 2 bitwise equal" >> "$out/${tag}_jacobi_split.log"
+  cmp /tmp/j0.bin /tmp/j4.bin >> "$out/${tag}_jacobi_split.log" 2>&1 && echo "split 4 bitwise equal" >> "$out/${tag}_jacobi_split.log"
+  rm -f /tmp/j0.bin /tmp/j2.bin /tmp/j4.bin
+  cat "$out/${tag}_jacobi_split.log"
+fi
+
 echo "== bench c2"
 timeout 400 python bench.py --steps 5 --warmup 3 > "$out/${tag}_bench_c2.json" 2> "$out/${tag}_bench_c2.err"
 echo "bench rc $?"

@@ -1512,6 +1512,21 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
   return 0;
 }
 
+namespace basd {
+// jacobi_oe8.cu, opt-in experiment (BASD_JACOBI_SPLIT=2|4): small full problems split over a cluster of
+// 2 or 4 CTAs with several CTAs resident per SM.  0 = off (the default).
+int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, float tol, int max_sweeps,
+                            int* sweeps_out, cudaStream_t st, int* rot_out, int csize);
+static int jacobi_split_csize() {
+  static const int v = [] {
+    const char* e = getenv("BASD_JACOBI_SPLIT");
+    const int c = e ? atoi(e) : 0;
+    return (c == 2 || c == 4) ? c : 0;
+  }();
+  return v;
+}
+}  // namespace basd
+
 // Orthogonalises the rows of each (n x m) row-major matrix in place. ld % 4 == 0 and
 // 16-byte aligned bases are required (128-bit row accesses).
 extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,
@@ -1536,7 +1551,7 @@ extern "C" int basd_jacobi_rows_ranked(float* G, int n, int m, int ld, long stri
   if (batch <= 0 || n <= 0) return 0;
   if ((ld & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(G) & 15)) return -3;
   static const bool no_oe8 = getenv("BASD_JACOBI_NO_OE8") != nullptr;
-  if (row_dims && !no_oe8 && n <= 256 && m <= 256) {
+  if (row_dims && !no_oe8 && n <= 256 && m <= 256 && !basd::jacobi_split_csize()) {
     const int e = launch_jacobi_oe8(G, n, m, ld, stride, batch, row_dims, tol, max_sweeps, sweeps_out,
                                     (cudaStream_t)stream, 0, 1 << 30, rot_out, 1);
     if (e != -100) return e;
@@ -1561,6 +1576,12 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
   const bool no_oddeven = getenv("BASD_JACOBI_ROUNDROBIN") != nullptr;
   // eight rows per 16-lane group (jacobi_oe8.cu): a quarter of the shared-memory exchange traffic
   static const bool no_oe8 = getenv("BASD_JACOBI_NO_OE8") != nullptr;
+  // opt-in experiment: full (dims == null) small problems split over 2 or 4 CTAs, several CTAs per SM
+  if (!dims && jacobi_split_csize() && n <= 256 && m <= 208) {
+    const int e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, tol, max_sweeps, sweeps_out, st, rot_out,
+                                          jacobi_split_csize());
+    if (e != -100) return e;
+  }
   if (!legacy && !no_oddeven && !no_oe8 && n <= 256 && m <= 256) {
     const int e = launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st,
                                     0, 1 << 30, rot_out);

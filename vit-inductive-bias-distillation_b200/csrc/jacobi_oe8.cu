@@ -396,11 +396,11 @@ __device__ __forceinline__ void angle_pass_ptr(float g_own, float& sn, float& sd
 }
 
 template <int G, int NF>
-__global__ void __launch_bounds__(192, 1)
-jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                               const int* __restrict__ dims, float tol, int max_sweeps,
-                               int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
-                               int* __restrict__ rot_out) {
+__device__ __forceinline__ void
+jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                             const int* __restrict__ dims, float tol, int max_sweeps,
+                             int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
+                             int* __restrict__ rot_out) {
   cg::cluster_group cluster = cg::this_cluster();
   const int csize = cluster.num_blocks(), crank = cluster.block_rank();
   extern __shared__ __align__(16) float smem[];
@@ -581,6 +581,65 @@ jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, 
 }
 
 template <int G, int NF>
+__global__ void __launch_bounds__(192, 1)
+jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                               const int* __restrict__ dims, float tol, int max_sweeps,
+                               int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
+                               int* __restrict__ rot_out) {
+  jacobi_rows_oe8_cluster_body<G, NF>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi,
+                                      rot_out);
+}
+
+// Opt-in experiment (BASD_JACOBI_SPLIT=2|4, not yet measured): the SAME cluster sweep for the small
+// per-sample problems (<= 256 rows, <= 208 columns), each problem split over 2 or 4 CTAs of at most
+// 224 threads and 144 registers so that TWO (or more) CTAs of different problems are resident per SM.
+// The single-CTA kernel above holds a whole problem in one SM's registers (13 warps x 128 registers =
+// the full register file) and measures ~50 % issue-slot utilisation: every warp of the SM waits on the
+// same dot -> reduce -> angle -> rotate chain at the same time.  Two independent half-problems per SM
+// have independent barriers, so one's latency chain can overlap the other's FMA phase.
+template <int G, int NF, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+jacobi_rows_oe8_split_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
+                             const int* __restrict__ dims, float tol, int max_sweeps,
+                             int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
+                             int* __restrict__ rot_out) {
+  jacobi_rows_oe8_cluster_body<G, NF>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi,
+                                      rot_out);
+}
+
+// MAXT / MINB: 224 threads x 2 CTAs per SM for halves (<= 14 groups per CTA), 128 threads x 3 CTAs per
+// SM for quarters (<= 8 groups per CTA: 168 registers, no spills at 13 floats per row piece).
+template <int NF, int MAXT, int MINB>
+static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
+                        int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize) {
+  constexpr int G = 16;
+  const int groups = (n + R - 1) / R;
+  int gpc = (groups + csize - 1) / csize;
+  gpc = (gpc + 1) & ~1;                                   // whole warps
+  const int threads = gpc * G;
+  if (threads > MAXT || threads < 32) return -100;
+  const size_t nslots = gpc + 1;
+  const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
+  auto kernel = jacobi_rows_oe8_split_kernel<G, NF, MAXT, MINB>;
+  BASD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(batch * csize);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BASD_CUDA(cudaLaunchKernelEx(&cfg, kernel, Gm, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, 0, 1 << 30,
+                               rot_out));
+  return 0;
+}
+
+template <int G, int NF>
 static int launch_cluster(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims,
                           float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                           int dim_hi, int* rot_out) {
@@ -670,6 +729,22 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
   BASD_OE8(16);
 #undef BASD_OE8W
 #undef BASD_OE8
+}
+
+// Opt-in split of the small problems over 2 or 4 CTAs (see jacobi_rows_oe8_split_kernel).  Full problems
+// only (no device-side sizes).  Returns -100 when the shape does not fit.
+int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, float tol, int max_sweeps,
+                            int* sweeps_out, cudaStream_t st, int* rot_out, int csize) {
+  if (n > 256 || m > 208 || (csize != 2 && csize != 4)) return -100;
+#define BASD_OE8S(NF)                                                                                      \
+  return csize == 2 ? oe8::launch_split<NF, 224, 2>(G, n, m, ld, stride, batch, nullptr, tol, max_sweeps,      \
+                                                    sweeps_out, st, rot_out, csize)                            \
+                    : oe8::launch_split<NF, 128, 3>(G, n, m, ld, stride, batch, nullptr, tol, max_sweeps,      \
+                                                    sweeps_out, st, rot_out, csize)
+  if (m <= 128) BASD_OE8S(8);
+  if (m <= 192) BASD_OE8S(12);
+  BASD_OE8S(13);
+#undef BASD_OE8S
 }
 
 // Cluster variant: up to 768 active rows; up to 384 active columns with 16-lane groups (portable
