@@ -18,6 +18,12 @@ if [ -x build/jacobi_check ]; then
   cmp /tmp/j0.bin /tmp/j4.bin >> "$out/${tag}_jacobi_split.log" 2>&1 && echo "split 4 bitwise equal" >> "$out/${tag}_jacobi_split.log"
   rm -f /tmp/j0.bin /tmp/j2.bin /tmp/j4.bin
   cat "$out/${tag}_jacobi_split.log"
+  echo "== register-resident pivoted Cholesky experiment: default vs BASD_CHOL_REG=1 (full rank, rank 48, n = 150)"
+  for args in "1024 196 384" "1024 196 48" "256 150 300"; do
+    timeout 30 build/jacobi_check chol $args
+    BASD_CHOL_REG=1 timeout 30 build/jacobi_check chol $args
+  done > "$out/${tag}_chol_reg.log" 2>&1
+  cat "$out/${tag}_chol_reg.log"
 fi
 
 echo "== bench c2"

@@ -1421,12 +1421,27 @@ static int launch_grouped(float* G, int n, int m, int ld, long stride, int batch
 
 }  // namespace basd
 
+namespace basd {
+// cholesky_reg.cu, opt-in experiment (BASD_CHOL_REG=1): register-resident left-looking pivoted Cholesky
+int launch_pivoted_cholesky_reg(const float* K, int n, int ld, long stride_k, float* LT, int ldl,
+                                long stride_l, int batch, float rel_tol, int* rank_out, const int* dims,
+                                cudaStream_t st);
+}  // namespace basd
+
 extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, float* LT, int ldl,
                                      long stride_l, int batch, float rel_tol, int* rank_out,
                                      const int* dims, void* stream) {
   using namespace basd;
   if (batch <= 0 || n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  {   // opt-in experiment (cholesky_reg.cu): factor rows resident in registers, not yet measured
+    static const bool reg = getenv("BASD_CHOL_REG") != nullptr;
+    if (reg) {
+      const int e = launch_pivoted_cholesky_reg(K, n, ld, stride_k, LT, ldl, stride_l, batch, rel_tol, rank_out,
+                                                dims, st);
+      if (e != -100) return e;
+    }
+  }
   {   // left-looking, four outputs per thread: factor rows resident in shared memory
     const size_t npad = ((size_t)n + 127) & ~(size_t)127;
     const int wpp = (int)(npad >> 7);
