@@ -1530,8 +1530,9 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
 namespace basd {
 // jacobi_oe8.cu, opt-in experiment (BASD_JACOBI_SPLIT=2|4): small full problems split over a cluster of
 // 2 or 4 CTAs with several CTAs resident per SM.  0 = off (the default).
-int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, float tol, int max_sweeps,
-                            int* sweeps_out, cudaStream_t st, int* rot_out, int csize);
+int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
+                            int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
+                            int dim_hi);
 static int jacobi_split_csize() {
   static const int v = [] {
     const char* e = getenv("BASD_JACOBI_SPLIT");
@@ -1593,8 +1594,8 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
   static const bool no_oe8 = getenv("BASD_JACOBI_NO_OE8") != nullptr;
   // opt-in experiment: full (dims == null) small problems split over 2 or 4 CTAs, several CTAs per SM
   if (!dims && jacobi_split_csize() && n <= 256 && m <= 208) {
-    const int e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, tol, max_sweeps, sweeps_out, st, rot_out,
-                                          jacobi_split_csize());
+    const int e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, nullptr, tol, max_sweeps, sweeps_out, st,
+                                          rot_out, jacobi_split_csize(), 0, 1 << 30);
     if (e != -100) return e;
   }
   if (!legacy && !no_oddeven && !no_oe8 && n <= 256 && m <= 256) {
@@ -1636,8 +1637,13 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
     // square problems with a device-side active size (k x k principal-angle SVDs): those with
     // k <= 200 run register/shared-memory resident, the rest on the cluster kernel below
     constexpr int SMALL = 200;
-    int e = no_oe8 ? -100 : launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
-                                             sweeps_out, st, 0, SMALL, rot_out);
+    int e = -100;
+    if (jacobi_split_csize())                              // opt-in experiment, see launch_jacobi_oe8_split
+      e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, rot_out,
+                                  jacobi_split_csize(), 0, SMALL);
+    if (e == -100)
+      e = no_oe8 ? -100 : launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
+                                            sweeps_out, st, 0, SMALL, rot_out);
     if (e == -100)
       e = launch_oddeven<8, 7, 800>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out,
                                     st, 0, SMALL, rot_out);

@@ -611,9 +611,11 @@ jacobi_rows_oe8_split_kernel(float* __restrict__ Gbase, int n, int m, int ld, lo
 // SM for quarters (<= 8 groups per CTA: 168 registers, no spills at 13 floats per row piece).
 template <int NF, int MAXT, int MINB>
 static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
-                        int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize) {
+                        int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
+                        int dim_hi) {
   constexpr int G = 16;
-  const int groups = (n + R - 1) / R;
+  const int cap = (dims && dim_hi < n) ? dim_hi : n;      // device-side sizes: problems outside the window exit
+  const int groups = (cap + R - 1) / R;
   int gpc = (groups + csize - 1) / csize;
   gpc = (gpc + 1) & ~1;                                   // whole warps
   const int threads = gpc * G;
@@ -634,7 +636,7 @@ static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BASD_CUDA(cudaLaunchKernelEx(&cfg, kernel, Gm, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, 0, 1 << 30,
+  BASD_CUDA(cudaLaunchKernelEx(&cfg, kernel, Gm, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi,
                                rot_out));
   return 0;
 }
@@ -731,18 +733,23 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
 #undef BASD_OE8
 }
 
-// Opt-in split of the small problems over 2 or 4 CTAs (see jacobi_rows_oe8_split_kernel).  Full problems
-// only (no device-side sizes).  Returns -100 when the shape does not fit.
-int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, float tol, int max_sweeps,
-                            int* sweeps_out, cudaStream_t st, int* rot_out, int csize) {
-  if (n > 256 || m > 208 || (csize != 2 && csize != 4)) return -100;
+// Opt-in split of the small problems over 2 or 4 CTAs (see jacobi_rows_oe8_split_kernel): full problems
+// (dims == null) or square problems with a device-side active size inside [dim_lo, dim_hi] (the k x k
+// principal-angle SVDs: 48 problems leave two thirds of the SMs idle on the single-CTA kernel).
+// Returns -100 when the shape does not fit.
+int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
+                            int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
+                            int dim_hi) {
+  const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
+  const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
+  if (cap_n > 256 || cap_m > 208 || (csize != 2 && csize != 4)) return -100;
 #define BASD_OE8S(NF)                                                                                      \
-  return csize == 2 ? oe8::launch_split<NF, 224, 2>(G, n, m, ld, stride, batch, nullptr, tol, max_sweeps,      \
-                                                    sweeps_out, st, rot_out, csize)                            \
-                    : oe8::launch_split<NF, 128, 3>(G, n, m, ld, stride, batch, nullptr, tol, max_sweeps,      \
-                                                    sweeps_out, st, rot_out, csize)
-  if (m <= 128) BASD_OE8S(8);
-  if (m <= 192) BASD_OE8S(12);
+  return csize == 2 ? oe8::launch_split<NF, 224, 2>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,         \
+                                                    sweeps_out, st, rot_out, csize, dim_lo, dim_hi)            \
+                    : oe8::launch_split<NF, 128, 3>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,         \
+                                                    sweeps_out, st, rot_out, csize, dim_lo, dim_hi)
+  if (cap_m <= 128) BASD_OE8S(8);
+  if (cap_m <= 192) BASD_OE8S(12);
   BASD_OE8S(13);
 #undef BASD_OE8S
 }
