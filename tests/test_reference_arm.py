@@ -75,3 +75,41 @@ def test_bench_reference_arm_is_rank0_only():
                          capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
     assert not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src", "losses")),
+                    reason="the reference tree only exists in the build container")
+def test_reference_checkpoint_state_loads_into_the_replacement(tmp_path):
+    """`accelerator.register_for_checkpointing(basd_loss)` (trainer.py:84) saves the module's
+    state_dict; a checkpoint written by the reference must load into the replacement (same keys, shapes,
+    dtypes), reproduce the reference's RNG-drawn projections and round-trip back into the reference."""
+    sys.path.insert(0, REFERENCE)
+    try:
+        from src.losses.combined import BASDLoss as RefLoss
+    finally:
+        sys.path.remove(REFERENCE)
+    from basd_b200.losses import BASDLoss
+    cfg = types.SimpleNamespace(num_extraction_points=4)
+    crit = torch.nn.CrossEntropyLoss()
+    torch.manual_seed(7)
+    ref = RefLoss(crit, 192, 384, 12, 64, config=cfg, teacher_has_cls_token=True)
+    with torch.no_grad():
+        ref.layer_selector.log_temperatures.copy_(torch.tensor([0.1, 0.5, 0.9, 1.3]))
+    path = tmp_path / "custom_checkpoint_0.pkl"
+    torch.save(ref.state_dict(), path)
+    torch.manual_seed(99)                                   # different draws: loading must overwrite them
+    mine = BASDLoss(crit, 192, 384, 12, 64, config=cfg, teacher_has_cls_token=True)
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    missing, unexpected = mine.load_state_dict(torch.load(path), strict=True)
+    assert not missing and not unexpected
+    for key, value in ref.state_dict().items():
+        got = mine.state_dict()[key]
+        assert got.dtype == value.dtype and got.shape == value.shape and torch.equal(got, value), key
+    assert mine.token_layers == ref.token_layers
+    assert [n for n, _ in mine.named_parameters()] == [n for n, _ in ref.named_parameters()]
+    ref.load_state_dict(mine.state_dict(), strict=True)     # and back
+    # same seed -> same projections as the reference draws them (orthogonal_ order, layer_selector.py:51-56)
+    torch.manual_seed(7)
+    again = BASDLoss(crit, 192, 384, 12, 64, config=cfg, teacher_has_cls_token=True)
+    assert torch.equal(again.layer_selector.proj_s, ref.layer_selector.proj_s)
+    assert torch.equal(again.layer_selector.proj_t, ref.layer_selector.proj_t)
