@@ -148,10 +148,13 @@ class GrassmannianLayerSelector(nn.Module):
         mixed attention maps keyed by student layer.  The weights come from the kernels;
         materialising the full mixed maps is only done here, for API compatibility --
         BASDLoss never does it."""
-        has_cls = True
+        # the mixing weights do not depend on the attention maps; the flag only tells the statistics
+        # stage how to read them: (B,H,N_t+1,N_t+1) maps carry a CLS row, (B,1,N_t,N_t) maps do not
+        keys = sorted(all_teacher_tokens.keys())
+        a0, n_t = all_teacher_attns[keys[0]], all_teacher_tokens[keys[0]].shape[1]
+        has_cls = not (a0.dim() == 4 and a0.shape[-1] == n_t)
         weights, _ = self.mixing_weights(student_tokens_per_layer, all_teacher_tokens,
                                          all_teacher_attns, extraction_indices, has_cls=has_cls)
-        keys = sorted(all_teacher_tokens.keys())
         tok = torch.stack([all_teacher_tokens[k] for k in keys])
         att = torch.stack([all_teacher_attns[k] for k in keys])
         mixed_tok, mixed_att = {}, {}
