@@ -33,3 +33,32 @@ def test_c4_against_live_oracle():
     if ranks_equal:
         assert cs.cosine(got["grad_log_temps"], ref["grad_log_temps"]) > COS_TOL
     assert torch.allclose(got["grad_logits"], ref["grad_logits"], atol=1e-6, rtol=1e-3)
+
+
+def test_selector_forward_returns_the_reference_shaped_dicts():
+    """Secondary entry of SURVEY 8(b): GrassmannianLayerSelector.forward -> (mixed tokens, mixed attention
+    maps) keyed by student layer (layer_selector.py:116-152), checked against the oracle's mixing weights."""
+    work = cs.workload("c1", 16)
+    inputs = syn.make_inputs(work, seed=4)
+    ref = cs.run_oracle(work, inputs)
+    logits, targets, st, te, at = inputs
+    mod = cs.build_cuda_module(work)
+    sel = mod.layer_selector
+    st_d = {k: v.cuda() for k, v in st.items()}
+    te_d = {k: v.cuda() for k, v in te.items()}
+    at_d = {k: v.cuda() for k, v in at.items()}
+    with torch.no_grad():
+        mixed_tok, mixed_att = sel(st_d, te_d, at_d, mod.token_layers)
+    assert sorted(mixed_tok) == sorted(mixed_att) == list(mod.token_layers)
+    keys = sorted(te)
+    tok = torch.stack([te[k].float() for k in keys])
+    att = torch.stack([at[k].float() for k in keys])
+    for i, layer in enumerate(mod.token_layers):
+        w = ref["weights"][i]
+        want_tok = (w.view(-1, 1, 1, 1) * tok).sum(0)
+        want_att = (w.view(-1, 1, 1, 1, 1) * att).sum(0)
+        assert mixed_tok[layer].shape == te[keys[0]].shape and mixed_att[layer].shape == at[keys[0]].shape
+        assert (mixed_tok[layer].float().cpu() - want_tok).abs().max() < 1e-3 * want_tok.abs().max()
+        assert (mixed_att[layer].float().cpu() - want_att).abs().max() < 1e-3 * want_att.abs().max()
+    assert [sel.subspace_ranks[k] for k in keys] == ref["ranks"] or _ranks_ok(
+        [sel.subspace_ranks[k] for k in keys], ref["ranks"], mod)
