@@ -21,10 +21,11 @@ if [ -x build/jacobi_check ]; then
   for sp in "" 2 4; do BASD_JACOBI_SPLIT=$sp timeout 20 build/jacobi_check /dev/null 48 384 384 174; done \
     >> "$out/${tag}_jacobi_split.log" 2>&1
   cat "$out/${tag}_jacobi_split.log"
-  echo "== register-resident pivoted Cholesky experiment: default vs BASD_CHOL_REG=1 (full rank, rank 48, n = 150)"
+  echo "== register-resident pivoted Cholesky experiment: default vs BASD_CHOL_REG=1|2 (full rank, rank 48, n = 150)"
   for args in "1024 196 384" "1024 196 48" "256 150 300"; do
     timeout 30 build/jacobi_check chol $args
-    BASD_CHOL_REG=1 timeout 30 build/jacobi_check chol $args
+    BASD_CHOL_REG=1 timeout 30 build/jacobi_check chol $args      # four lanes per row
+    BASD_CHOL_REG=2 timeout 30 build/jacobi_check chol $args      # two lanes per row
   done > "$out/${tag}_chol_reg.log" 2>&1
   cat "$out/${tag}_chol_reg.log"
 fi

@@ -86,7 +86,7 @@ static int chol_main(int argc, char** argv) {
   long rsum = 0;
   for (int v : rank) rsum += v;
   std::printf("chol reg=%s batch %d n %d inner %d: %.3f ms per launch, rank[0] %d rank[last] %d rank sum %ld, "
-              "max |LT^T LT - K| / max |K| = %.2e\n", std::getenv("BASD_CHOL_REG") ? "1" : "0", batch, n, inner,
+              "max |LT^T LT - K| / max |K| = %.2e\n", std::getenv("BASD_CHOL_REG") ? std::getenv("BASD_CHOL_REG") : "0", batch, n, inner,
               best, rank[0], rank[batch - 1], rsum, worst / kmax);
   return 0;
 }

@@ -20,11 +20,12 @@
 namespace basd {
 namespace chreg {
 
-constexpr int LPR = 4;            // lanes per row
-constexpr int GW = 16;            // columns per group: 4 lanes x 4 floats
+constexpr int GW = 16;            // columns per group: LPR lanes x (16 / LPR) floats
 
-template <int NG>                 // column groups: n <= 16 NG
-__global__ void __maxnreg__(80)
+// LPR lanes own a row: 4 (800 threads, 52 data registers) or 2 (416 threads, 104 data registers: half the
+// warps, so the per-step overhead -- pivot reduction, quad reduce, argmax, barriers -- is issued half as often)
+template <int NG, int LPR>        // column groups: n <= 16 NG
+__global__ void __maxnreg__(LPR == 4 ? 80 : 152)
 pivoted_cholesky_reg_kernel(const float* __restrict__ Kbase, int n, int ld, long strideK,
                             float* __restrict__ LTbase, int ldl, long strideL, float rel_tol,
                             int* __restrict__ rank_out, const int* __restrict__ dims) {
@@ -50,9 +51,12 @@ pivoted_cholesky_reg_kernel(const float* __restrict__ Kbase, int n, int ld, long
     idx = __shfl_sync(0xffffffffu, idx_in, __ffs(who) - 1);
   };
 
-  float4 l[NG];                                           // this lane's slice of row i of L
+  constexpr int W = GW / LPR, NV = W / 4;                 // floats / float4s per lane per group
+  float4 l[NG][NV];                                       // this lane's slice of row i of L
 #pragma unroll
-  for (int g = 0; g < NG; ++g) l[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) l[g][v] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int e = tid; e < nn * nn; e += T) {
     const int r = e / nn, c = e - r * nn;
     Ks[e] = Kg[(long)r * ld + c];
@@ -77,9 +81,9 @@ pivoted_cholesky_reg_kernel(const float* __restrict__ Kbase, int n, int ld, long
 #pragma unroll 1
     for (int jq = 0; jq < LPR && !done; ++jq) {           // the lane that receives the new entries
 #pragma unroll
-      for (int js = 0; js < 4; ++js) {                    // ... in component js of its l[g]
+      for (int js = 0; js < W; ++js) {                    // ... in slot js of its l[g]
         if (done) break;
-        const int j = GW * g + 4 * jq + js;
+        const int j = GW * g + W * jq + js;
         if (j >= nn) { done = true; break; }
         unsigned vb;
         int p;
@@ -96,21 +100,26 @@ pivoted_cholesky_reg_kernel(const float* __restrict__ Kbase, int n, int ld, long
         const float kp = live_row ? Ks[p * nn + i] : 0.f;
         if (i == p) {
 #pragma unroll
-          for (int gg = 0; gg <= g; ++gg) *reinterpret_cast<float4*>(prow + GW * gg + 4 * q) = l[gg];
+          for (int gg = 0; gg <= g; ++gg)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) *reinterpret_cast<float4*>(prow + GW * gg + W * q + 4 * v) = l[gg][v];
         }
         __syncthreads();
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
         for (int gg = 0; gg <= g; ++gg) {
-          const float4 pv = *reinterpret_cast<const float4*>(prow + GW * gg + 4 * q);
-          a0 = fmaf(l[gg].x, pv.x, a0);
-          a1 = fmaf(l[gg].y, pv.y, a1);
-          a2 = fmaf(l[gg].z, pv.z, a2);
-          a3 = fmaf(l[gg].w, pv.w, a3);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const float4 pv = *reinterpret_cast<const float4*>(prow + GW * gg + W * q + 4 * v);
+            a0 = fmaf(l[gg][v].x, pv.x, a0);
+            a1 = fmaf(l[gg][v].y, pv.y, a1);
+            a2 = fmaf(l[gg][v].z, pv.z, a2);
+            a3 = fmaf(l[gg][v].w, pv.w, a3);
+          }
         }
         float acc = (a0 + a1) + (a2 + a3);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (LPR == 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         float c = 0.f, nd = -1.f;
         if (live_row && di >= 0.f) {
           const float rs = rsqrtf(best);
@@ -118,11 +127,11 @@ pivoted_cholesky_reg_kernel(const float* __restrict__ Kbase, int n, int ld, long
           nd = (i == p) ? -1.f : fmaxf(fmaf(-c, c, di), 0.f);
           di = nd;
         }
-        if (q == jq) {                                    // static slot: component js of group g
-          if (js == 0) l[g].x = c;
-          else if (js == 1) l[g].y = c;
-          else if (js == 2) l[g].z = c;
-          else l[g].w = c;
+        if (q == jq) {                                    // static slot: component js % 4 of l[g][js / 4]
+          if ((js & 3) == 0) l[g][js >> 2].x = c;
+          else if ((js & 3) == 1) l[g][js >> 2].y = c;
+          else if ((js & 3) == 2) l[g][js >> 2].z = c;
+          else l[g][js >> 2].w = c;
         }
         if (q == 0 && live_row) LT[(long)j * ldl + i] = c;
         {
@@ -146,18 +155,26 @@ pivoted_cholesky_reg_kernel(const float* __restrict__ Kbase, int n, int ld, long
 
 }  // namespace chreg
 
-// 128 < n <= 200 (800 threads, 80 registers each); returns -100 when the shape does not fit (the caller falls back to the
-// shared-memory kernels).
+// 128 < n <= 200 with four lanes per row (800 threads, 80 registers), n <= 208 with two (416 threads);
+// returns -100 when the shape does not fit (the caller falls back to the shared-memory kernels).
 int launch_pivoted_cholesky_reg(const float* K, int n, int ld, long stride_k, float* LT, int ldl,
                                 long stride_l, int batch, float rel_tol, int* rank_out, const int* dims,
-                                cudaStream_t st) {
-  if (n <= 128 || n > 200) return -100;
-  const int rows = (n + 7) & ~7;                          // whole warps of row quads
+                                cudaStream_t st, int lanes_per_row) {
+  if (n <= 128 || n > (lanes_per_row == 2 ? 208 : 200)) return -100;
   const size_t dyn = (size_t)n * n * sizeof(float);
-  BASD_CUDA(cudaFuncSetAttribute(chreg::pivoted_cholesky_reg_kernel<13>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  chreg::pivoted_cholesky_reg_kernel<13><<<batch, rows * chreg::LPR, dyn, st>>>(K, n, ld, stride_k, LT, ldl,
-                                                                             stride_l, rel_tol, rank_out, dims);
+  if (lanes_per_row == 2) {
+    const int rows = (n + 15) & ~15;                      // whole warps of row pairs
+    BASD_CUDA(cudaFuncSetAttribute(chreg::pivoted_cholesky_reg_kernel<13, 2>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    chreg::pivoted_cholesky_reg_kernel<13, 2><<<batch, rows * 2, dyn, st>>>(K, n, ld, stride_k, LT, ldl, stride_l,
+                                                                         rel_tol, rank_out, dims);
+  } else {
+    const int rows = (n + 7) & ~7;                        // whole warps of row quads
+    BASD_CUDA(cudaFuncSetAttribute(chreg::pivoted_cholesky_reg_kernel<13, 4>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    chreg::pivoted_cholesky_reg_kernel<13, 4><<<batch, rows * 4, dyn, st>>>(K, n, ld, stride_k, LT, ldl, stride_l,
+                                                                         rel_tol, rank_out, dims);
+  }
   BASD_LAUNCH_CHECK();
   return 0;
 }

@@ -1425,7 +1425,7 @@ namespace basd {
 // cholesky_reg.cu, opt-in experiment (BASD_CHOL_REG=1): register-resident left-looking pivoted Cholesky
 int launch_pivoted_cholesky_reg(const float* K, int n, int ld, long stride_k, float* LT, int ldl,
                                 long stride_l, int batch, float rel_tol, int* rank_out, const int* dims,
-                                cudaStream_t st);
+                                cudaStream_t st, int lanes_per_row);
 }  // namespace basd
 
 extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, float* LT, int ldl,
@@ -1435,10 +1435,10 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
   if (batch <= 0 || n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   {   // opt-in experiment (cholesky_reg.cu): factor rows resident in registers, not yet measured
-    static const bool reg = getenv("BASD_CHOL_REG") != nullptr;
+    static const int reg = getenv("BASD_CHOL_REG") ? atoi(getenv("BASD_CHOL_REG")) : 0;   // 1 or 4: four lanes per row, 2: two
     if (reg) {
       const int e = launch_pivoted_cholesky_reg(K, n, ld, stride_k, LT, ldl, stride_l, batch, rel_tol, rank_out,
-                                                dims, st);
+                                                dims, st, reg == 2 ? 2 : 4);
       if (e != -100) return e;
     }
   }
