@@ -57,3 +57,20 @@ echo "== pytest -m gpu"
 timeout 1500 python -m pytest tests -m gpu -x -q > "$out/${tag}_pytest_gpu.log" 2>&1
 echo "pytest rc $?"
 tail -5 "$out/${tag}_pytest_gpu.log"
+
+echo "== one-pass weight-gradient experiment (BASD_WGRAD_ONEPASS=1): kernel test, then its time in the bench timeline"
+BASD_WGRAD_ONEPASS=1 timeout 400 python -m pytest tests/test_kernels_gpu.py -q -k "mix_interp_and_weight_grad" \
+  > "$out/${tag}_wgrad_onepass_test.log" 2>&1
+echo "one-pass kernel test rc $?"; tail -2 "$out/${tag}_wgrad_onepass_test.log"
+BASD_WGRAD_ONEPASS=1 timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline \
+  > "$out/${tag}_bench_c2_wgrad_onepass.json" 2> "$out/${tag}_bench_c2_wgrad_onepass.err"
+python - "$out/${tag}_bench_c2.json" "$out/${tag}_bench_c2_wgrad_onepass.json" <<'PY'
+import json, sys
+for path in sys.argv[1:]:
+    try:
+        d = json.load(open(path))
+        wg = [k for k in d.get("kernels", []) if k["kernel"] == "basd_weight_grad"]
+        print(path, "ms/step", d["ms_per_step"], "weight_grad ms", wg[0]["ms"] if wg else None)
+    except Exception as e:
+        print(path, "unreadable:", e)
+PY

@@ -245,6 +245,104 @@ weight_grad_kernel(LayerPtrs layers, int E, const float* __restrict__ Z, int B, 
   }
 }
 
+// Opt-in experiment (BASD_WGRAD_ONEPASS=1, not yet measured): the same partial sums with the upstream
+// gradient read ONCE.  weight_grad_kernel above runs one block column per teacher layer, so every block
+// column re-reads its slice of Z (E*B*N*D fp32, 616 MB at C2) -- ncu shows 2.4x the algorithmic DRAM
+// bytes.  Here a thread keeps its E x 8 values of Z in registers and walks LC teacher layers with them,
+// accumulating E x LC partial sums (48 registers for E = 4, LC = 12); grid = (slices, ceil(L / LC)).
+template <typename TIn, int EC, int LC>
+__global__ void __launch_bounds__(256)
+weight_grad_onepass_kernel(LayerPtrs layers, int L, int E, const float* __restrict__ Z, int B, int n_src,
+                           int n_dst, int D, float* __restrict__ partial) {
+  __shared__ float red[8][EC * LC];
+  const int l0 = blockIdx.y * LC;
+  const int groups = D >> 3;
+  const long total = (long)B * n_dst * groups;
+  const long slab = (long)B * n_dst * D;
+  float acc[EC][LC];
+#pragma unroll
+  for (int i = 0; i < EC; ++i)
+#pragma unroll
+    for (int k = 0; k < LC; ++k) acc[i][k] = 0.f;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int g = idx % groups;
+    const long tok = idx / groups;
+    const int n = tok % n_dst;
+    const int b = tok / n_dst;
+    int lo, hi;
+    float f;
+    taps(n, n_src, n_dst, lo, hi, f);
+    const long off_lo = ((long)b * n_src + lo) * D + g * 8;
+    const long off_hi = ((long)b * n_src + hi) * D + g * 8;
+    const long o = ((long)b * n_dst + n) * D + g * 8;
+    float z[EC][8];
+#pragma unroll
+    for (int i = 0; i < EC; ++i) {
+      if (i < E) {
+        const float4* zp = reinterpret_cast<const float4*>(Z + (long)i * slab + o);
+        const float4 z0 = __ldg(zp), z1 = __ldg(zp + 1);
+        z[i][0] = z0.x; z[i][1] = z0.y; z[i][2] = z0.z; z[i][3] = z0.w;
+        z[i][4] = z1.x; z[i][5] = z1.y; z[i][6] = z1.z; z[i][7] = z1.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) z[i][c] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LC; ++k) {
+      if (l0 + k < L) {
+        const TIn* src = reinterpret_cast<const TIn*>(layers.p[l0 + k]);
+        float v[8];
+        if (sizeof(TIn) == 2) {
+          load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_lo, v);
+          if (f != 0.f) {
+            float u[8];
+            load8(reinterpret_cast<const __nv_bfloat16*>(src) + off_hi, u);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = fmaf(f, u[c] - v[c], v[c]);
+          }
+        } else {
+          const float* p = reinterpret_cast<const float*>(src);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = p[off_lo + c];
+          if (f != 0.f) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = fmaf(f, p[off_hi + c] - v[c], v[c]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < EC; ++i) {
+          float sum = acc[i][k];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) sum = fmaf(z[i][c], v[c], sum);
+          acc[i][k] = sum;
+        }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < EC; ++i)
+#pragma unroll
+    for (int k = 0; k < LC; ++k) {
+      float v = acc[i][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][i * LC + k] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < EC * LC) {
+    const int i = threadIdx.x / LC, k = threadIdx.x % LC;
+    if (i < E && l0 + k < L) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+      partial[((long)blockIdx.x * L + (l0 + k)) * E + i] = v;
+    }
+  }
+}
+
 // d_weights[i,l] = sum_slices partial + sum_{b,n} gw[i,b,n] * resample(rows[l,b,:])[n]
 __global__ void weight_grad_finish_kernel(const float* __restrict__ partial, int slices,
                                           const float* __restrict__ gw,
@@ -354,6 +452,21 @@ extern "C" int basd_weight_grad(const void* const* teacher_layers, int L, int E,
   LayerPtrs lp;
   if (int rc = fill_layers(lp, teacher_layers, L)) return rc;
   const int slices = basd_weight_grad_slices();
+  static const bool onepass = getenv("BASD_WGRAD_ONEPASS") != nullptr;   // opt-in experiment, see the kernel
+  if (onepass && E <= 4) {
+    constexpr int LC = 12;
+    dim3 g1(slices, (L + LC - 1) / LC);
+    if (in_dtype == BASD_DTYPE_BF16)
+      weight_grad_onepass_kernel<__nv_bfloat16, 4, LC><<<g1, 256, 0, ST>>>(lp, L, E, Z, B, n_src, n_dst, D, partial);
+    else
+      weight_grad_onepass_kernel<float, 4, LC><<<g1, 256, 0, ST>>>(lp, L, E, Z, B, n_src, n_dst, D, partial);
+    BASD_LAUNCH_CHECK();
+    dim3 fg(L, E);
+    weight_grad_finish_kernel<<<fg, 256, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_src, n_dst, gw_scale,
+                                                 gw_scale_dev, d_weights);
+    BASD_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(slices, L);
   if (in_dtype == BASD_DTYPE_BF16)
     weight_grad_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>(lp, E, Z, B, n_src, n_dst, D, partial);
