@@ -1,7 +1,8 @@
 #!/usr/bin/env bash
 # One gpurun call that banks the round's baseline evidence before any kernel work:
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round_start.sh r2'
-# Order = value per GPU-minute: bench line, ncu launch list, full captures, then the GPU test suite.
+# Order = value per GPU-minute: the torch-free kernel A/Bs (seconds), bench line, ncu launch list, full captures,
+# the GPU test suite, then the remaining opt-in experiment that needs torch.
 # On a fresh box the first `import torch` + eager module loading + backbone features take ~2 min,
 # so no step gets less than 300 s (round 1 lost its last launch-list refresh to a 110 s limit).
 set -u
