@@ -21,6 +21,9 @@ if [ -x build/jacobi_check ]; then
   # the k x k principal-angle SVD shape: 48 problems, 384-wide allocation, active size 174
   for sp in "" 2 4; do BASD_JACOBI_SPLIT=$sp timeout 20 build/jacobi_check /dev/null 48 384 384 174; done \
     >> "$out/${tag}_jacobi_split.log" 2>&1
+  # the rank-aware entry point (C3: 48 non-zero rows of 196)
+  for sp in "" 2 4; do BASD_JACOBI_SPLIT=$sp timeout 20 build/jacobi_check /dev/null 1024 196 196 0 48; done \
+    >> "$out/${tag}_jacobi_split.log" 2>&1
   cat "$out/${tag}_jacobi_split.log"
   echo "== register-resident pivoted Cholesky experiment: default vs BASD_CHOL_REG=1|2 (full rank, rank 48, n = 150)"
   for args in "1024 196 384" "1024 196 48" "256 150 300"; do

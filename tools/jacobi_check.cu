@@ -100,6 +100,9 @@ int main(int argc, char** argv) {
   // optional 5th argument k: square problems allocated n x n (n == m) with a device-side active size k,
   // the shape of the k x k principal-angle SVDs (e.g. `48 384 384 174`)
   const int kdim = argc > 5 ? std::atoi(argv[5]) : 0;
+  // optional 6th argument r (with k = 0): only the first r rows are non-zero and the rank-aware entry point
+  // basd_jacobi_rows_ranked is called with row_dims = r (C3: a 49-token teacher resampled to 196: `1024 196 196 0 48`)
+  const int rdim = argc > 6 ? std::atoi(argv[6]) : 0;
   const size_t per = (size_t)n * m, total = per * batch;
   std::vector<float> host(total);
   // graded rows (like a product of two pivoted-Cholesky factors) plus a dense coupling
@@ -110,7 +113,7 @@ int main(int argc, char** argv) {
       const float scale = std::pow(10.f, -3.f * i / n);
       for (int j = 0; j < m; ++j) {
         const float v = scale * (rnd() + (i == j ? 2.f : 0.f));
-        host[b * per + (size_t)i * m + j] = (kdim && (i >= kdim || j >= kdim)) ? 0.f : v;
+        host[b * per + (size_t)i * m + j] = ((kdim && (i >= kdim || j >= kdim)) || (rdim && i >= rdim)) ? 0.f : v;
       }
     }
   float *d_in = nullptr, *d_work = nullptr;
@@ -119,8 +122,8 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&d_work, total * sizeof(float)));
   CK(cudaMalloc(&d_sweeps, batch * sizeof(int)));
   int* d_dims = nullptr;
-  if (kdim) {
-    std::vector<int> hd(batch, kdim);
+  if (kdim || rdim) {
+    std::vector<int> hd(batch, kdim ? kdim : rdim);
     CK(cudaMalloc(&d_dims, batch * sizeof(int)));
     CK(cudaMemcpy(d_dims, hd.data(), batch * sizeof(int), cudaMemcpyHostToDevice));
   }
@@ -133,7 +136,9 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(d_work, d_in, total * sizeof(float), cudaMemcpyDeviceToDevice));
     CK(cudaMemset(d_sweeps, 0, batch * sizeof(int)));
     CK(cudaEventRecord(e0, 0));
-    const int rc = basd_jacobi_rows(d_work, n, m, m, (long)per, batch, d_dims, 1e-6f, 18, d_sweeps, nullptr);
+    const int rc = rdim ? basd_jacobi_rows_ranked(d_work, n, m, m, (long)per, batch, d_dims, 1e-6f, 18, d_sweeps,
+                                                  nullptr, nullptr)
+                        : basd_jacobi_rows(d_work, n, m, m, (long)per, batch, d_dims, 1e-6f, 18, d_sweeps, nullptr);
     CK(cudaEventRecord(e1, 0));
     if (rc) { std::fprintf(stderr, "basd_jacobi_rows rc %d\n", rc); return 3; }
     CK(cudaEventSynchronize(e1));
@@ -157,8 +162,8 @@ int main(int argc, char** argv) {
       worst = std::fmax(worst, std::fabs(d) / (nr[i] * nr[k]));
     }
   }
-  std::printf("split=%s batch %d n %d m %d k %d: %.3f ms per launch, sweeps mean %.2f, max |cos| %.2e\n",
-              std::getenv("BASD_JACOBI_SPLIT") ? std::getenv("BASD_JACOBI_SPLIT") : "0", batch, n, m, kdim, best,
+  std::printf("split=%s batch %d n %d m %d k %d r %d: %.3f ms per launch, sweeps mean %.2f, max |cos| %.2e\n",
+              std::getenv("BASD_JACOBI_SPLIT") ? std::getenv("BASD_JACOBI_SPLIT") : "0", batch, n, m, kdim, rdim, best,
               mean / batch, worst);
   FILE* f = std::fopen(out, "wb");
   if (!f) return 4;

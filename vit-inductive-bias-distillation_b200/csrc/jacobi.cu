@@ -1532,7 +1532,7 @@ namespace basd {
 // 2 or 4 CTAs with several CTAs resident per SM.  0 = off (the default).
 int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
                             int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
-                            int dim_hi);
+                            int dim_hi, int rows_only = 0);
 static int jacobi_split_csize() {
   static const int v = [] {
     const char* e = getenv("BASD_JACOBI_SPLIT");
@@ -1567,6 +1567,11 @@ extern "C" int basd_jacobi_rows_ranked(float* G, int n, int m, int ld, long stri
   if (batch <= 0 || n <= 0) return 0;
   if ((ld & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(G) & 15)) return -3;
   static const bool no_oe8 = getenv("BASD_JACOBI_NO_OE8") != nullptr;
+  if (row_dims && basd::jacobi_split_csize() && n <= 256 && m <= 208) {   // opt-in experiment (rank-aware split)
+    const int e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, row_dims, tol, max_sweeps, sweeps_out,
+                                          (cudaStream_t)stream, rot_out, basd::jacobi_split_csize(), 0, 1 << 30, 1);
+    if (e != -100) return e;
+  }
   if (row_dims && !no_oe8 && n <= 256 && m <= 256 && !basd::jacobi_split_csize()) {
     const int e = launch_jacobi_oe8(G, n, m, ld, stride, batch, row_dims, tol, max_sweeps, sweeps_out,
                                     (cudaStream_t)stream, 0, 1 << 30, rot_out, 1);

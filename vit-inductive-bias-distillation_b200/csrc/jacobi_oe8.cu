@@ -395,7 +395,9 @@ __device__ __forceinline__ void angle_pass_ptr(float g_own, float& sn, float& sd
   }
 }
 
-template <int G, int NF>
+// RO ("rows only", split kernel): dims[problem] is the number of leading non-zero ROWS of a rank-deficient
+// factor product (rounded up to even, all columns active, no size window) instead of a square active size.
+template <int G, int NF, bool RO = false>
 __device__ __forceinline__ void
 jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                              const int* __restrict__ dims, float tol, int max_sweeps,
@@ -407,13 +409,13 @@ jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, lo
   __shared__ float red_scratch[32];
   __shared__ int cflag[2];
   const int prob = blockIdx.x / csize, tid = threadIdx.x;
-  if (dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;     // whole cluster exits together
+  if (!RO && dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;     // whole cluster exits together
   const int gpc = blockDim.x / G;
   const int lgid = tid / G, gl = tid % G;
   const int gid = crank * gpc + lgid;
   float* Gg = Gbase + (long)prob * stride;
-  const int nn = dims ? min(dims[prob], n) : n;
-  const int mm = dims ? min(dims[prob], m) : m;
+  const int nn = dims ? min(RO ? ((dims[prob] + 1) & ~1) : dims[prob], n) : n;
+  const int mm = (dims && !RO) ? min(dims[prob], m) : m;
   const int groups = (nn + R - 1) / R;
   const int cnt = max(0, min(R, nn - gid * R));
   constexpr int PITCH = NF * G;
@@ -597,24 +599,24 @@ jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, 
 // the full register file) and measures ~50 % issue-slot utilisation: every warp of the SM waits on the
 // same dot -> reduce -> angle -> rotate chain at the same time.  Two independent half-problems per SM
 // have independent barriers, so one's latency chain can overlap the other's FMA phase.
-template <int G, int NF, int MAXT, int MINB>
+template <int G, int NF, int MAXT, int MINB, bool RO>
 __global__ void __launch_bounds__(MAXT, MINB)
 jacobi_rows_oe8_split_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                              const int* __restrict__ dims, float tol, int max_sweeps,
                              int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
                              int* __restrict__ rot_out) {
-  jacobi_rows_oe8_cluster_body<G, NF>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi,
-                                      rot_out);
+  jacobi_rows_oe8_cluster_body<G, NF, RO>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo,
+                                          dim_hi, rot_out);
 }
 
 // MAXT / MINB: 224 threads x 2 CTAs per SM for halves (<= 14 groups per CTA), 128 threads x 3 CTAs per
 // SM for quarters (<= 8 groups per CTA: 168 registers, no spills at 13 floats per row piece).
-template <int NF, int MAXT, int MINB>
+template <int NF, int MAXT, int MINB, bool RO>
 static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
                         int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
                         int dim_hi) {
   constexpr int G = 16;
-  const int cap = (dims && dim_hi < n) ? dim_hi : n;      // device-side sizes: problems outside the window exit
+  const int cap = (!RO && dims && dim_hi < n) ? dim_hi : n;   // device-side sizes: problems outside the window exit
   const int groups = (cap + R - 1) / R;
   int gpc = (groups + csize - 1) / csize;
   gpc = (gpc + 1) & ~1;                                   // whole warps
@@ -622,7 +624,7 @@ static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch,
   if (threads > MAXT || threads < 32) return -100;
   const size_t nslots = gpc + 1;
   const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
-  auto kernel = jacobi_rows_oe8_split_kernel<G, NF, MAXT, MINB>;
+  auto kernel = jacobi_rows_oe8_split_kernel<G, NF, MAXT, MINB, RO>;
   BASD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(batch * csize);
@@ -739,19 +741,24 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
 // Returns -100 when the shape does not fit.
 int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
                             int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
-                            int dim_hi) {
-  const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
-  const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
+                            int dim_hi, int rows_only) {
+  const bool ro = rows_only && dims;
+  const int cap_n = (!ro && dims && dim_hi < n) ? dim_hi : n;
+  const int cap_m = (!ro && dims && dim_hi < m) ? dim_hi : m;
   if (cap_n > 256 || cap_m > 208 || (csize != 2 && csize != 4)) return -100;
-#define BASD_OE8S(NF)                                                                                      \
-  return csize == 2 ? oe8::launch_split<NF, 224, 2>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,         \
-                                                    sweeps_out, st, rot_out, csize, dim_lo, dim_hi)            \
-                    : oe8::launch_split<NF, 128, 3>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,         \
-                                                    sweeps_out, st, rot_out, csize, dim_lo, dim_hi)
-  if (cap_m <= 128) BASD_OE8S(8);
-  if (cap_m <= 192) BASD_OE8S(12);
+#define BASD_OE8S2(NF, RO)                                                                                 \
+  return csize == 2 ? oe8::launch_split<NF, 224, 2, RO>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,     \
+                                                        sweeps_out, st, rot_out, csize, dim_lo, dim_hi)        \
+                    : oe8::launch_split<NF, 128, 3, RO>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,     \
+                                                        sweeps_out, st, rot_out, csize, dim_lo, dim_hi)
+#define BASD_OE8S(NF)         \
+  if (ro) BASD_OE8S2(NF, true); \
+  BASD_OE8S2(NF, false)
+  if (cap_m <= 128) { BASD_OE8S(8); }
+  if (cap_m <= 192) { BASD_OE8S(12); }
   BASD_OE8S(13);
 #undef BASD_OE8S
+#undef BASD_OE8S2
 }
 
 // Cluster variant: up to 768 active rows; up to 384 active columns with 16-lane groups (portable
