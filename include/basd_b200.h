@@ -161,11 +161,13 @@ int basd_mix_rows(const float* rows, const float* weights, int E, int L, int B, 
                   int n_dst, float* w_out, float* totals, void* stream);
 
 /* dL/dweights[i,l] = <Z_i, resample(teacher_l)> + gw_scale * <gw_i, resample(rows_l)>.
- * partial: scratch of basd_weight_grad_slices() * L * E floats. */
+ * partial: scratch of basd_weight_grad_slices() * L * E floats.  n_src = tokens per teacher layer,
+ * n_rows = length of the importance rows (B, n_rows): the attention map's own token count, which
+ * differs from n_src when the tokens were resampled by the caller (relational.py:29-32). */
 int basd_weight_grad_slices(void);
 int basd_weight_grad(const void* const* teacher_layers, int L, int E, const float* Z,
-                     const float* gw, const float* rows, int in_dtype, int B, int n_src, int n_dst,
-                     int D, float gw_scale, const float* gw_scale_dev, float* partial,
+                     const float* gw, const float* rows, int in_dtype, int B, int n_src, int n_rows,
+                     int n_dst, int D, float gw_scale, const float* gw_scale_dev, float* partial,
                      float* d_weights, void* stream);
 
 /* ---- tensor-core batched GEMM (gemm_tc3.cu) ----------------------------------------- */

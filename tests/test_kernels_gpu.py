@@ -233,7 +233,7 @@ def test_mix_interp_and_weight_grad(dtype, n_src, n_dst):
     dw = torch.empty(e, l, device=DEV)
     sc = torch.tensor([0.7], device=DEV)
     call("basd_weight_grad", ptrs, l, e, ptr(z), ptr(gw), ptr(rows), dtype_code(layers[0]), b, n_src,
-         n_dst, d, 0.5, ptr(sc), ptr(partial), ptr(dw), stream())
+         n_src, n_dst, d, 0.5, ptr(sc), ptr(partial), ptr(dw), stream())
     lo, hi, fr = km.interp_taps(n_src, n_dst)
     lo, hi, fr = lo.to(DEV), hi.to(DEV), fr.to(DEV)
     for j in range(l):

@@ -120,3 +120,68 @@ def test_standalone_entry_points():
     assert marchenko_pastur_rank(feats.cuda()) == rp.mp_rank(feats)
     x = torch.randn(3, 49, 64)
     assert (_align_token_count(x.cuda(), 196).cpu() - rp.align_tokens(x, 196)).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("side,has_cls", [(257, True), (50, True), (49, False), (256, False)])
+def test_standalone_loss_resamples_the_attention_row(side, has_cls):
+    """relational.py:29-32: the attention map keeps the teacher's own token count while the tokens
+    arrive already aligned to the student's (DINOv2 257 x 257 map against 196 tokens, a 7 x 7 CNN
+    map against 196 tokens): the importance row is resampled to N_s, never written at N_s width."""
+    from basd_b200.losses import geometric_relational_loss
+    from oracle import ref_port as rp
+    torch.manual_seed(side)
+    b, n, ds, dt, heads = 3, 196, 64, 96, 2
+    s = torch.randn(b, n, ds)
+    t = torch.randn(b, n, dt)
+    attn = torch.softmax(2.0 * torch.randn(b, heads, side, side), -1)
+    sg = s.clone().requires_grad_(True)
+    ref = rp.procrustes_loss(sg, t, attn, has_cls)
+    ref.backward()
+    sd = s.cuda().requires_grad_(True)
+    got = geometric_relational_loss(sd, t.cuda(), attn.cuda(), has_cls_token=has_cls)
+    got.backward()
+    torch.cuda.synchronize()
+    assert abs(float(got) - float(ref)) / abs(float(ref)) < LOSS_TOL
+    assert cs.cosine(sd.grad.cpu(), sg.grad) > COS_TOL
+
+
+def test_shape_errors_are_raised_before_any_kernel_runs():
+    """Mistakes the reference reports as torch shape errors (layer_selector.py:72,128-129,
+    relational.py:47) must not reach the raw-pointer kernels."""
+    work = cs.workload("c1", 4)
+    inputs = syn.make_inputs(work, seed=0)
+    logits, targets, st, te, at = [x if not isinstance(x, dict) else {k: v.cuda() for k, v in x.items()}
+                                   for x in inputs]
+    mod = cs.build_cuda_module(work)
+    lg, tg = logits.cuda(), targets.cuda()
+    layers = mod.token_layers
+
+    def run(st_=st, te_=te, at_=at):
+        return mod(lg, tg, st_, te_, at_)
+
+    with pytest.raises(ValueError, match="num_student_tokens"):          # CLS not stripped
+        bad = dict(st)
+        bad = {k: torch.cat([v[:, :1], v], 1) for k, v in bad.items()}
+        run(st_=bad)
+    with pytest.raises(ValueError, match="share one shape"):             # ragged teacher layers
+        bad = dict(te)
+        bad[0] = bad[0][:, :-1]
+        run(te_=bad)
+    with pytest.raises(ValueError, match="share one shape"):             # mixed dtypes
+        bad = dict(te)
+        bad[1] = bad[1].bfloat16()
+        run(te_=bad)
+    with pytest.raises(ValueError, match="token count"):                 # attention maps of two sizes
+        bad = dict(at)
+        bad[0] = bad[0][:, :, :-1, :-1]
+        run(at_=bad)
+    with pytest.raises(ValueError, match="batch"):
+        bad = {k: v[:-1] for k, v in te.items()}
+        run(te_=bad)
+    with pytest.raises(ValueError, match="attention maps"):
+        bad = {k: v for k, v in at.items() if k != 0}
+        run(at_=bad)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        run(st_={k: v.cpu() for k, v in st.items()})
+    loss = run()                                                          # and the module still works
+    assert torch.isfinite(loss) and layers == mod.token_layers

@@ -17,8 +17,7 @@ if __name__ == "__main__":
         rel = abs(float(got["loss"]) - float(ref["loss"])) / abs(float(ref["loss"]))
         werr = float((got["weights"] - ref["weights"]).abs().max())
         cos = min(cs.cosine(got["grad_students"][l], ref["grad_students"][l]) for l in ref["layers"])
-        sw = got["module"].layer_selector.last_step.procrustes.sweeps.float() if hasattr(
-            got["module"].layer_selector, "last_step") else None
+        sw = got["module"].layer_selector.last_state.sweeps["procrustes"].float()
         print(f"{key} b{batch}: loss rel {rel:.2e}  weights {werr:.2e}  min grad cos {cos:.6f}  "
               f"ranks equal {got['ranks'] == ref['ranks']}"
               + (f"  sweeps mean {float(sw.mean()):.2f}" if sw is not None else ""))

@@ -85,8 +85,8 @@ static int chol_main(int argc, char** argv) {
   }
   long rsum = 0;
   for (int v : rank) rsum += v;
-  std::printf("chol reg=%s batch %d n %d inner %d: %.3f ms per launch, rank[0] %d rank[last] %d rank sum %ld, "
-              "max |LT^T LT - K| / max |K| = %.2e\n", std::getenv("BASD_CHOL_REG") ? std::getenv("BASD_CHOL_REG") : "0", batch, n, inner,
+  std::printf("chol %s batch %d n %d inner %d: %.3f ms per launch, rank[0] %d rank[last] %d rank sum %ld, "
+              "max |LT^T LT - K| / max |K| = %.2e\n", "lib", batch, n, inner,
               best, rank[0], rank[batch - 1], rsum, worst / kmax);
   return 0;
 }
@@ -162,8 +162,8 @@ int main(int argc, char** argv) {
       worst = std::fmax(worst, std::fabs(d) / (nr[i] * nr[k]));
     }
   }
-  std::printf("split=%s batch %d n %d m %d k %d r %d: %.3f ms per launch, sweeps mean %.2f, max |cos| %.2e\n",
-              std::getenv("BASD_JACOBI_SPLIT") ? std::getenv("BASD_JACOBI_SPLIT") : "0", batch, n, m, kdim, rdim, best,
+  std::printf("jacobi %s batch %d n %d m %d k %d r %d: %.3f ms per launch, sweeps mean %.2f, max |cos| %.2e\n",
+              "lib", batch, n, m, kdim, rdim, best,
               mean / batch, worst);
   FILE* f = std::fopen(out, "wb");
   if (!f) return 4;

@@ -20,35 +20,36 @@ from ._native import call, ptr, stream
 
 import os as _os
 
-JACOBI_TOL = float(_os.environ.get("BASD_JACOBI_TOL", 1e-6))
-JACOBI_SWEEPS = int(_os.environ.get("BASD_JACOBI_SWEEPS", 18))
-# per-sample Procrustes SVDs: sigma is re-measured from P^T X (second-order accurate) and the polar
-# factor is insensitive to rotations inside clusters, so the sweep may stop one level earlier
-PROC_JACOBI_TOL = float(_os.environ.get("BASD_PROC_JACOBI_TOL", 1e-6))
+# Numerical constants of the path (how each was chosen: DESIGN.md section 3.3; the sweeps that
+# measured them: tests/tools/floor_sweep.py, tests/tools/parity_report.py).
+JACOBI_TOL = 1e-6        # |cos| between two rows below which they count as orthogonal
+JACOBI_SWEEPS = 18       # sweep cap (C2 backbone features converge in 8-11)
+PROC_JACOBI_TOL = 1e-6   # per-sample Procrustes SVDs: loosening costs gradient parity before it saves a sweep
 CHOL_TOL = 1e-5          # pivoted-Cholesky rank cut (per-sample N x N Grams), relative to the
                          # largest diagonal: just above the fp32 accumulation noise of K
 GRAM_CHOL_TOL = 1e-7     # same for the D x D selector Grams
 SV_FLOOR = 1e-6          # k x k principal-angle SVD: directions below this are dropped
-SHARD_SELECTOR_EIG = _os.environ.get("BASD_NO_SELECTOR_SHARDING") is None
-SHARD_WAVE_CTAS = int(_os.environ.get("BASD_SHARD_WAVE_CTAS", 148))
 ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerically zero in fp32
 # Procrustes with a Gram side: singular directions of G = F_q^T F_p below this fraction of sigma_max
 # leave the polar factor.  The factors are already cut at sqrt(CHOL_TOL) = 3e-3 of their own largest
 # direction, so G's spectrum ends near 1e-5 by itself.  2.5e-4 (the first choice) dropped directions the
 # reference keeps: per-sample tokens with condition number 2e3 gave gradient cosine 0.99909, 0.99999
-# at 1e-5, with every well-conditioned case unchanged (tests/tools/floor_sweep.py, measured on B200).
-PROC_SV_FLOOR = float(_os.environ.get("BASD_PROC_SV_FLOOR", 1e-5))
+# at 1e-5, with every well-conditioned case unchanged (measured on B200).
+PROC_SV_FLOOR = 1e-5
 # ... except for the side whose vectors are derived (q_j = normalise(G p_j), direction error
 # eps sigma_max / sigma_j) when they enter a Gram-side operator sum_j (F_q q_j)(F_q q_j)^T / sigma_j:
 # at 1e-5 the teacher-token gradient of ill-conditioned tokens came out 41x too large (B200)
-PROC_SV_FLOOR_DERIVED = float(_os.environ.get("BASD_PROC_SV_FLOOR_DERIVED", 2.5e-4))
+PROC_SV_FLOOR_DERIVED = 2.5e-4
 # both sides direct (no Gram): q_j = normalise(G p_j) is recovered with noise ~eps*sqrt(K)*sigma_max/sigma_j;
-# measured on B200 (tests/tools/debug_edge.py n256): 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
-MIXED_DIRECT_RATIO = float(_os.environ.get("BASD_MIXED_DIRECT_RATIO", 2.0))
-PROC_SV_FLOOR_DIRECT = float(_os.environ.get("BASD_DIRECT_FLOOR", 3e-5))
-# Equal factor widths (both sides Gram factors): which side's factor indexes the Jacobi rows.
-# "narrow" = the side with the smaller token dimension (see procrustes_forward), "teacher" = old rule.
-PROC_TIE_Q = _os.environ.get("BASD_PROC_TIE_Q", "narrow")
+# measured on B200: 1e-6 -> cosine 0.998, 1e-5 -> 0.9998, 3e-5 -> 0.9999, 1e-4 -> 0.9996
+PROC_SV_FLOOR_DIRECT = 3e-5
+MIXED_DIRECT_RATIO = 2.0
+# Equal factor widths (both sides Gram factors): the side with the smaller token dimension indexes the
+# Jacobi rows (see procrustes_forward)
+PROC_TIE_Q = "narrow"
+# problems of one selector launch are dealt to the data-parallel ranks once they exceed one wave
+SHARD_SELECTOR_EIG = _os.environ.get("BASD_NO_SELECTOR_SHARDING") is None
+SHARD_WAVE_CTAS = 148
 
 
 def _f32(*shape, device):
@@ -222,6 +223,43 @@ def _all_reduce(flat: torch.Tensor, group):
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
 
 
+def importance_rows(attns, b: int, has_cls: bool, dev) -> torch.Tensor:
+    """(L, B, n_rows) fp32 importance rows: the CLS query row averaged over heads, or the mean over
+    heads and queries without a CLS token (relational.py:22-27).  n_rows is the ATTENTION map's own
+    token count (side minus the CLS column); it equals the teacher token count inside BASDLoss and
+    may differ from it in the stand-alone loss, whose tokens arrive already resampled
+    (relational.py:29-32) -- the mixing and gradient kernels resample the row to the student grid."""
+    widths = set()
+    for a in attns:
+        if a.shape[0] != b:
+            raise ValueError(f"attention batch {a.shape[0]} differs from the token batch {b}")
+        if a.dim() == 2:
+            widths.add(a.shape[1])
+        elif a.dim() in (3, 4):
+            widths.add(a.shape[-1] - (1 if has_cls else 0))
+        else:
+            raise ValueError(f"attention must be (B,H,Q,K), (B,H,K) or a (B,N) row, got {tuple(a.shape)}")
+    if len(widths) != 1:
+        raise ValueError(f"teacher attention maps disagree on the token count: {sorted(widths)}")
+    n_rows = widths.pop()
+    if n_rows < 1:
+        raise ValueError("attention map has no token columns")
+    rows = _f32(len(attns), b, n_rows, device=dev)
+    for j, a in enumerate(attns):
+        a = a if a.is_contiguous() else a.contiguous()
+        if a.dim() == 2:      # already an importance row (B, n_rows): "next" row f1 of SURVEY §8
+            rows[j].copy_(a)
+            continue
+        if a.dim() == 3:      # (B, H, side): only the CLS query row was handed over
+            _, h, side = a.shape
+            q_rows = 1
+        else:
+            _, h, q_rows, side = a.shape
+        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, q_rows, int(has_cls),
+             ptr(rows[j]), stream())
+    return rows
+
+
 def statistics(students, teachers, attns, has_cls):
     dev = students[0].device
     e, l = len(students), len(teachers)
@@ -241,41 +279,14 @@ def statistics(students, teachers, attns, has_cls):
         token_gram(s, gram_s[i], col_s[i])
     for j, t in enumerate(teachers):
         token_gram(t, gram_t[j], col_t[j])
-    rows = _f32(l, b, n_t, device=dev)
-    for j, a in enumerate(attns):
-        a = a if a.is_contiguous() else a.contiguous()
-        if a.dim() == 2:      # already an importance row (B, Nt): "next" row f1 of SURVEY §8
-            rows[j].copy_(a)
-            continue
-        if a.dim() == 3:      # (B, H, side): only the CLS query row was handed over
-            _, h, side = a.shape
-            q_rows = 1
-        else:
-            _, h, q_rows, side = a.shape
-        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, q_rows, int(has_cls),
-             ptr(rows[j]), stream())
+    rows = importance_rows(attns, b, has_cls, dev)
     return Stats(gram_s, col_s, gram_t, col_t, rows), flat
 
 
 def attention_only_stats(teachers, attns, has_cls):
     """Importance rows only (stand-alone Procrustes use: no selector statistics needed)."""
-    dev = teachers[0].device
-    l = len(teachers)
-    b, n_t, _ = teachers[0].shape
-    rows = _f32(l, b, n_t, device=dev)
-    for j, a in enumerate(attns):
-        a = a if a.is_contiguous() else a.contiguous()
-        if a.dim() == 2:
-            rows[j].copy_(a)
-            continue
-        if a.dim() == 3:      # (B, H, side): only the CLS query row was handed over
-            _, h, side = a.shape
-            q_rows = 1
-        else:
-            _, h, q_rows, side = a.shape
-        call("basd_attn_rows", ptr(a), nat.dtype_code(a), b, h, side, q_rows, int(has_cls),
-             ptr(rows[j]), stream())
-    return Stats(None, None, None, None, rows)
+    b = teachers[0].shape[0]
+    return Stats(None, None, None, None, importance_rows(attns, b, has_cls, teachers[0].device))
 
 
 @dataclass
@@ -442,7 +453,8 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
          ptr(aligned), nat.dtype_code(aligned), stream())
     w = _f32(e, b, n, device=dev)
     totals = _f32(e, b, device=dev)
-    call("basd_mix_rows", ptr(stats.rows), ptr(weights), e, l, b, n_t, n, ptr(w), ptr(totals), stream())
+    call("basd_mix_rows", ptr(stats.rows), ptr(weights), e, l, b, stats.rows.shape[2], n, ptr(w), ptr(totals),
+         stream())
 
     a = _f32(e, b, n, d_s, device=dev)
     bm = _f32(e, b, n, d_t, device=dev)
@@ -595,8 +607,8 @@ def procrustes_backward(students, teachers, stats: Stats, pro: ProcrustesState,
     d_weights = _f32(e, l, device=dev)
     tptrs = (nat.C.c_void_p * l)(*[t.data_ptr() for t in teachers])
     call("basd_weight_grad", tptrs, l, e, ptr(z), ptr(pro.gw), ptr(stats.rows),
-         nat.dtype_code(teachers[0]), b, n_t, n, d_t, scale, ptr(go), ptr(partial), ptr(d_weights),
-         stream())
+         nat.dtype_code(teachers[0]), b, n_t, stats.rows.shape[2], n, d_t, scale, ptr(go), ptr(partial),
+         ptr(d_weights), stream())
     return outs, d_weights, (z if want_teacher_grad else None)
 
 

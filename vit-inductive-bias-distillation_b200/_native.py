@@ -47,7 +47,7 @@ _SIG = {
     "basd_mix_interp": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p],
     "basd_mix_rows": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "basd_weight_grad_slices": [],
-    "basd_weight_grad": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],
+    "basd_weight_grad": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],
     "basd_weighted_center": [_p, _i, _l, _p, _l, _i, _i, _p, _l, _i, _p],
     "basd_extract_diag": [_p, _i, _i, _l, _i, _p, _p],
     "basd_procrustes_rows_finish": [_p, _i, _i, _l, _p, _i, _i, _l, _i, _f, _f, _i, _i, _p, _p, _p, _p],

@@ -1,9 +1,10 @@
 // Register-resident, left-looking, diagonally pivoted Cholesky for the per-sample N x N Grams
-// (opt-in: BASD_CHOL_REG=1; written after round 1's GPU budget was spent -- not yet measured).
+// (128 < n <= 208; measured on B200, 1,024 x 196^2: 1.73 ms for the shared-memory kernel it replaced,
+// 1.37 ms with four lanes per row, 1.18 ms with two -- the default; n = 150, 256 problems: 0.34 / 0.22 /
+// 0.20 ms).
 //
-// pivoted_cholesky_left4_kernel (jacobi.cu) keeps the factor in shared memory and re-reads all j
-// finished columns at step j: ~100 KB of shared-memory traffic per step at n = 196, ~2,400 cycles per
-// step measured.  Here every row i of L lives in the REGISTERS of the four lanes that own the row
+// The shared-memory kernel re-read all j finished columns at step j: ~100 KB of shared-memory traffic per
+// step at n = 196, ~2,400 cycles per step measured.  Here every row i of L lives in the REGISTERS of the four lanes that own the row
 // (lane q of the quad holds columns 16 g + 4 q .. + 3 of every 16-column group g), so a step only
 // moves the pivot row: its four owners publish L[p][0 .. 16 (g + 1)) to shared memory, everyone
 // reads it back as broadcast 128-bit loads and forms its row's dot product with (g + 1) x 4 FMAs.
@@ -25,7 +26,7 @@ constexpr int GW = 16;            // columns per group: LPR lanes x (16 / LPR) f
 // LPR lanes own a row: 4 (800 threads, 52 data registers) or 2 (416 threads, 104 data registers: half the
 // warps, so the per-step overhead -- pivot reduction, quad reduce, argmax, barriers -- is issued half as often)
 template <int NG, int LPR>        // column groups: n <= 16 NG
-__global__ void __maxnreg__(LPR == 4 ? 80 : 152)
+__global__ void __maxnreg__(LPR == 4 ? 72 : 128)   // warps are allocated in fours: 28 x 32 x 72 and 16 x 32 x 128 registers fit the SM
 pivoted_cholesky_reg_kernel(const float* __restrict__ Kbase, int n, int ld, long strideK,
                             float* __restrict__ LTbase, int ldl, long strideL, float rel_tol,
                             int* __restrict__ rank_out, const int* __restrict__ dims) {

@@ -470,8 +470,7 @@ static int launch_sgemm_type(int M, int N, int K, const void* A, int lda, long s
                              const float* a_shift, const float* B, int ldb, long sB, float* C,
                              int ldc, long sC, int batch, float alpha, const float* alpha_dev,
                              float beta, cudaStream_t st) {
-  static const bool small_only = getenv("BASD_SGEMM_SMALL") != nullptr;   // A/B aid
-  if (!small_only && M >= 96 && N >= 96) {
+  if (M >= 96 && N >= 96) {
     const int tm8 = pick_tile8(M), tn8 = pick_tile8(N);
 #define BASD_ARGS8 M, N, K, A, lda, sA, a_shift, B, ldb, sB, C, ldc, sC, batch, alpha, alpha_dev, beta, st
     if (tm8 == 104 && tn8 == 104) return launch_sgemm8_tile<TA, TB, AT, 104, 104>(BASD_ARGS8);

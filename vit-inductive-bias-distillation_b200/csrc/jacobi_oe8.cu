@@ -26,6 +26,13 @@ namespace oe8 {
 
 constexpr int R = 8;      // rows per group
 
+// Floats per shared-memory row.  A warp of 16-lane groups touches two consecutive rows at once
+// (lane gl of both groups reads column gl + 16 j): their banks differ only if the pitch is an odd
+// multiple of 16.  ncu on the 384-column eigenproblems (pitch 384): 39 % of the shared-memory
+// wavefronts were 2-way conflicts.
+template <int G, int NF>
+__host__ __device__ constexpr int row_pitch() { return (G == 16 && (NF * G) % 32 == 0) ? NF * G + 16 : NF * G; }
+
 struct RowState { float n, d; };   // squared norm of the actual row, scale (actual = d * stored)
 
 template <int NF>
@@ -89,11 +96,17 @@ __device__ __forceinline__ void angle(float ga, RowState& sx, RowState& sy, bool
 }
 
 // stored x <- stored y + t1 stored x ; stored y <- stored x - t2 stored y  (rows trade places)
-template <int NF>
+// DESC walks the elements downwards.  Both outputs of an element need both inputs, so the first result
+// lands in a spare register and the register file's view of the x row shifts by one register per pass;
+// a second pass in the opposite direction shifts it back, so a loop body made of one ascending and one
+// descending full step is a closed permutation (no register moves at the back edge: ptxas emitted ~50
+// MOVs per half-step for the all-ascending body).
+template <int NF, bool DESC = false>
 __device__ __forceinline__ void apply(float (&x)[NF], float (&y)[NF], bool valid, float t1, float t2) {
   if (!valid) return;
 #pragma unroll
-  for (int e = 0; e < NF; ++e) {
+  for (int i = 0; i < NF; ++i) {
+    const int e = DESC ? NF - 1 - i : i;
     const float a = x[e], b = y[e];
     x[e] = fmaf(t1, a, b);
     y[e] = fmaf(-t2, b, a);
@@ -144,7 +157,7 @@ __device__ __forceinline__ float sel4(const float (&v)[4], int k) {
 // One angle pass of a step with parity ODD: lane p (p < 8, parity of p = ODD) owns the pair
 // (p, p + 1); position 0 (even steps) and the right neighbour's position 0 (odd steps) keep
 // their state in shared memory.
-template <int G, int ODD>
+template <int G, int ODD, bool FULL = false>
 __device__ __forceinline__ void angle_pass(float g_own, float& sn, float& sd, float2* xs,
                                            int slot, int right, int gl, int cnt, bool cross_ok,
                                            float tol2, float zero_thr, float& worst, int& nrot,
@@ -157,7 +170,7 @@ __device__ __forceinline__ void angle_pass(float g_own, float& sn, float& sd, fl
   RowState sx{sn, sd}, sy{pn, pd};
   if (from_smem_x) { const float2 v = xs[slot]; sx.n = v.x; sx.d = v.y; }
   if (from_smem_y) { const float2 v = xs[right]; sy.n = v.x; sy.d = v.y; }
-  const bool valid = owner && (from_smem_y ? cross_ok : (gl + 1 < cnt));
+  const bool valid = FULL ? owner : (owner && (from_smem_y ? cross_ok : (gl + 1 < cnt)));
   float t1, t2;
   angle(g_own, sx, sy, valid, tol2, zero_thr, worst, nrot, t1, t2);
   // new states: x's position keeps sx, the partner position receives sy
@@ -172,6 +185,88 @@ __device__ __forceinline__ void angle_pass(float g_own, float& sn, float& sd, fl
   for (int k = 0; k < 4; ++k) {
     T1[k] = __shfl_sync(0xffffffffu, t1, 2 * k + ODD, G);
     T2[k] = __shfl_sync(0xffffffffu, t2, 2 * k + ODD, G);
+  }
+}
+
+// The half-steps of one sweep.  FULL: every position of both groups of the warp exists and has a right
+// neighbour (all but the last warp of a problem): the validity predicates are compile-time true, so
+// the rotated rows trade places without the per-thread branches (and the register shuffling ptxas
+// emits at their reconvergence points).  Both instantiations execute the same block-wide barriers.
+template <int G, int NF, bool FULL, bool DESC>
+__device__ __forceinline__ void full_step(float (&r)[R - 1][NF], float& sn, float& sd, float2* xs, int slot,
+                                          int right, float* my_row, float* right_row, int gl, int cnt,
+                                          bool cross_ok, bool has_odd, float tol2, float zero_thr, float& worst,
+                                          int& nrot) {
+  float ga[4], T1[4], T2[4];
+  // ---------------- even step: (0,1) with position 0 in shared memory, (2,3) (4,5) (6,7)
+  ga[0] = dot_smem<G, NF>(my_row, r[0]);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) ga[k] = dot_local<NF>(r[2 * k - 1], r[2 * k]);
+  angle_pass<G, 0, FULL>(reduce4_owner<G>(ga, gl), sn, sd, xs, slot, right, gl, cnt, cross_ok, tol2, zero_thr, worst,
+                         nrot, T1, T2);
+  if (FULL || 1 < cnt) {
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const float a = my_row[G * j], b = r[0][j];
+      my_row[G * j] = fmaf(T1[0], a, b);
+      r[0][j] = fmaf(-T2[0], b, a);
+    }
+  }
+#pragma unroll
+  for (int k = 1; k < 4; ++k) apply<NF, DESC>(r[2 * k - 1], r[2 * k], FULL || 2 * k + 1 < cnt, T1[k], T2[k]);
+  __syncthreads();
+  // ---------------- odd step: (1,2) (3,4) (5,6), (7, right neighbour's 0) through shared memory
+  if (FULL || has_odd) {
+    ga[3] = dot_smem<G, NF>(right_row, r[R - 2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ga[k] = dot_local<NF>(r[2 * k], r[2 * k + 1]);
+    angle_pass<G, 1, FULL>(reduce4_owner<G>(ga, gl), sn, sd, xs, slot, right, gl, cnt, cross_ok, tol2, zero_thr,
+                           worst, nrot, T1, T2);
+    if (FULL || cross_ok) {
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const int j = DESC ? NF - 1 - i : i;
+        const float a = r[R - 2][j], b = right_row[G * j];
+        r[R - 2][j] = fmaf(T1[3], a, b);
+        right_row[G * j] = fmaf(-T2[3], b, a);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) apply<NF, DESC>(r[2 * k], r[2 * k + 1], FULL || 2 * k + 2 < cnt, T1[k], T2[k]);
+  }
+  __syncthreads();
+}
+
+// The half-steps of one sweep.  FULL: every position of both groups of the warp exists and has a right
+// neighbour and the row count is even (all but the last warp of a problem): the validity predicates are
+// compile-time true.  Both instantiations execute the same block-wide barriers.
+template <int G, int NF, bool FULL>
+__device__ __forceinline__ void sweep_steps(float (&r)[R - 1][NF], float& sn, float& sd, float2* xs, int slot,
+                                            int right, float* my_row, float* right_row, int gl, int cnt,
+                                            bool cross_ok, int nn, float tol2, float zero_thr, float& worst,
+                                            int& nrot) {
+#pragma unroll 1
+  for (int step = 0; step < nn; step += 4) {
+    if ((step & 15) == 0 && step) {                  // fold the scales (they shrink by c per rotation)
+      const float d0 = xs[slot].y;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NF; ++j) my_row[G * j] *= d0;
+      if (gl == 0) xs[slot].y = 1.f;
+#pragma unroll
+      for (int i = 0; i < R - 1; ++i) {
+        const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
+#pragma unroll
+        for (int e = 0; e < NF; ++e) r[i][e] *= di;
+      }
+      sd = 1.f;
+      __syncwarp();
+    }
+    full_step<G, NF, FULL, false>(r, sn, sd, xs, slot, right, my_row, right_row, gl, cnt, cross_ok, step + 1 < nn,
+                                  tol2, zero_thr, worst, nrot);
+    if (step + 2 < nn)
+      full_step<G, NF, FULL, true>(r, sn, sd, xs, slot, right, my_row, right_row, gl, cnt, cross_ok, step + 3 < nn,
+                                   tol2, zero_thr, worst, nrot);
   }
 }
 
@@ -202,7 +297,7 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
   const int mm = (dims && !rows_only) ? min(dims[prob], m) : m;
   const int groups = (nn + R - 1) / R;
   const int cnt = max(0, min(R, nn - gid * R));          // positions of this group that exist
-  constexpr int PITCH = NF * G;                          // floats per shared-memory row
+  constexpr int PITCH = row_pitch<G, NF>();               // floats per shared-memory row
   const int nslots = blockDim.x / G + 1;
   float2* xs = reinterpret_cast<float2*>(smem + (size_t)nslots * PITCH);   // state of every position 0
   const int slot = min(gid, nslots - 1);
@@ -227,6 +322,7 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
     }
   }
   const bool cross_ok = (cnt == R) && (gid + 1 < groups);   // right neighbour always owns a position 0
+  const bool full_warp = __all_sync(0xffffffffu, cross_ok) && !(nn & 1);
   const float tol2 = tol * tol;
   int nrot = 0;
   int sweep = 0;
@@ -272,59 +368,12 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
     const float mx = block_max(mxl, red_scratch);        // (also orders the shared-memory writes above)
     const float zero_thr = 1e-14f * mx;
     float worst = 0.f;
-#pragma unroll 2     // 4 measured no faster (17.9 vs 17.8 ms)
-    for (int step = 0; step < nn; step += 2) {
-      float ga[4], T1[4], T2[4];
-      // ---------------- even step: (0,1) with position 0 in shared memory, (2,3) (4,5) (6,7)
-      if ((step & 15) == 0 && step) {                  // fold the scales (they shrink by c per rotation)
-        const float d0 = xs[slot].y;
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < NF; ++j) my_row[G * j] *= d0;
-        if (gl == 0) xs[slot].y = 1.f;
-#pragma unroll
-        for (int i = 0; i < R - 1; ++i) {
-          const float di = __shfl_sync(0xffffffffu, sd, i + 1, G);
-#pragma unroll
-          for (int e = 0; e < NF; ++e) r[i][e] *= di;
-        }
-        sd = 1.f;
-        __syncwarp();
-      }
-      ga[0] = dot_smem<G, NF>(my_row, r[0]);
-#pragma unroll
-      for (int k = 1; k < 4; ++k) ga[k] = dot_local<NF>(r[2 * k - 1], r[2 * k]);
-      angle_pass<G, 0>(reduce4_owner<G>(ga, gl), sn, sd, xs, slot, right, gl, cnt, cross_ok, tol2, zero_thr, worst, nrot, T1, T2);
-      if (1 < cnt) {
-#pragma unroll
-        for (int j = 0; j < NF; ++j) {
-          const float a = my_row[G * j], b = r[0][j];
-          my_row[G * j] = fmaf(T1[0], a, b);
-          r[0][j] = fmaf(-T2[0], b, a);
-        }
-      }
-#pragma unroll
-      for (int k = 1; k < 4; ++k) apply<NF>(r[2 * k - 1], r[2 * k], 2 * k + 1 < cnt, T1[k], T2[k]);
-      __syncthreads();
-      // ---------------- odd step: (1,2) (3,4) (5,6), (7, right neighbour's 0) through shared memory
-      if (step + 1 < nn) {
-        ga[3] = dot_smem<G, NF>(right_row, r[R - 2]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ga[k] = dot_local<NF>(r[2 * k], r[2 * k + 1]);
-        angle_pass<G, 1>(reduce4_owner<G>(ga, gl), sn, sd, xs, slot, right, gl, cnt, cross_ok, tol2, zero_thr, worst, nrot, T1, T2);
-        if (cross_ok) {
-#pragma unroll
-          for (int j = 0; j < NF; ++j) {
-            const float a = r[R - 2][j], b = right_row[G * j];
-            r[R - 2][j] = fmaf(T1[3], a, b);
-            right_row[G * j] = fmaf(-T2[3], b, a);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) apply<NF>(r[2 * k], r[2 * k + 1], 2 * k + 2 < cnt, T1[k], T2[k]);
-      }
-      __syncthreads();
-    }
+    if (full_warp)
+      sweep_steps<G, NF, true>(r, sn, sd, xs, slot, right, my_row, right_row, gl, cnt, cross_ok, nn, tol2, zero_thr,
+                               worst, nrot);
+    else
+      sweep_steps<G, NF, false>(r, sn, sd, xs, slot, right, my_row, right_row, gl, cnt, cross_ok, nn, tol2, zero_thr,
+                                worst, nrot);
     worst = block_max(worst, red_scratch);
     if (worst < tol) { ++sweep; break; }
   }
@@ -395,9 +444,7 @@ __device__ __forceinline__ void angle_pass_ptr(float g_own, float& sn, float& sd
   }
 }
 
-// RO ("rows only", split kernel): dims[problem] is the number of leading non-zero ROWS of a rank-deficient
-// factor product (rounded up to even, all columns active, no size window) instead of a square active size.
-template <int G, int NF, bool RO = false>
+template <int G, int NF>
 __device__ __forceinline__ void
 jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                              const int* __restrict__ dims, float tol, int max_sweeps,
@@ -409,16 +456,16 @@ jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, lo
   __shared__ float red_scratch[32];
   __shared__ int cflag[2];
   const int prob = blockIdx.x / csize, tid = threadIdx.x;
-  if (!RO && dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;     // whole cluster exits together
+  if (dims && (dims[prob] < dim_lo || dims[prob] > dim_hi)) return;            // whole cluster exits together
   const int gpc = blockDim.x / G;
   const int lgid = tid / G, gl = tid % G;
   const int gid = crank * gpc + lgid;
   float* Gg = Gbase + (long)prob * stride;
-  const int nn = dims ? min(RO ? ((dims[prob] + 1) & ~1) : dims[prob], n) : n;
-  const int mm = (dims && !RO) ? min(dims[prob], m) : m;
+  const int nn = dims ? min(dims[prob], n) : n;
+  const int mm = dims ? min(dims[prob], m) : m;
   const int groups = (nn + R - 1) / R;
   const int cnt = max(0, min(R, nn - gid * R));
-  constexpr int PITCH = NF * G;
+  constexpr int PITCH = row_pitch<G, NF>();
   const int nslots = gpc + 1;                            // + a spare nobody pairs with
   float2* xs = reinterpret_cast<float2*>(smem + (size_t)nslots * PITCH);
   float* my_row = smem + (size_t)lgid * PITCH + gl;
@@ -592,39 +639,38 @@ jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, 
                                       rot_out);
 }
 
-// Opt-in experiment (BASD_JACOBI_SPLIT=2|4, not yet measured): the SAME cluster sweep for the small
-// per-sample problems (<= 256 rows, <= 208 columns), each problem split over 2 or 4 CTAs of at most
-// 224 threads and 144 registers so that TWO (or more) CTAs of different problems are resident per SM.
-// The single-CTA kernel above holds a whole problem in one SM's registers (13 warps x 128 registers =
-// the full register file) and measures ~50 % issue-slot utilisation: every warp of the SM waits on the
-// same dot -> reduce -> angle -> rotate chain at the same time.  Two independent half-problems per SM
-// have independent barriers, so one's latency chain can overlap the other's FMA phase.
-template <int G, int NF, int MAXT, int MINB, bool RO>
+// The SAME cluster sweep for small problems (<= 256 rows, <= 208 columns), each split over 4 CTAs of at
+// most 128 threads so that a launch with FEW problems spreads over four times the SMs (the k x k
+// principal-angle SVDs, 48 problems at C2: 2.21 -> 1.64 ms on B200).  Measured and rejected for full waves
+// of problems (1,024 x 196^2: 19.4 ms with quarters, 21.3 ms with halves, 16.1 ms on the single-CTA
+// kernel: the cluster barrier and the DSMEM hop of the boundary row cost more than the independent
+// barriers of co-resident CTAs gain); results are bitwise equal to the single-CTA kernel's.
+template <int G, int NF, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 jacobi_rows_oe8_split_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
                              const int* __restrict__ dims, float tol, int max_sweeps,
                              int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
                              int* __restrict__ rot_out) {
-  jacobi_rows_oe8_cluster_body<G, NF, RO>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo,
-                                          dim_hi, rot_out);
+  jacobi_rows_oe8_cluster_body<G, NF>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi,
+                                      rot_out);
 }
 
-// MAXT / MINB: 224 threads x 2 CTAs per SM for halves (<= 14 groups per CTA), 128 threads x 3 CTAs per
-// SM for quarters (<= 8 groups per CTA: 168 registers, no spills at 13 floats per row piece).
-template <int NF, int MAXT, int MINB, bool RO>
+// MAXT / MINB: 128 threads x 3 CTAs per SM (<= 8 groups per CTA: 168 registers, no spills at 13 floats
+// per row piece).
+template <int NF, int MAXT, int MINB>
 static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
                         int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
                         int dim_hi) {
   constexpr int G = 16;
-  const int cap = (!RO && dims && dim_hi < n) ? dim_hi : n;   // device-side sizes: problems outside the window exit
+  const int cap = (dims && dim_hi < n) ? dim_hi : n;          // device-side sizes: problems outside the window exit
   const int groups = (cap + R - 1) / R;
   int gpc = (groups + csize - 1) / csize;
   gpc = (gpc + 1) & ~1;                                   // whole warps
   const int threads = gpc * G;
   if (threads > MAXT || threads < 32) return -100;
   const size_t nslots = gpc + 1;
-  const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
-  auto kernel = jacobi_rows_oe8_split_kernel<G, NF, MAXT, MINB, RO>;
+  const size_t dyn = (nslots * row_pitch<G, NF>() + 2 * nslots + 4) * sizeof(float);
+  auto kernel = jacobi_rows_oe8_split_kernel<G, NF, MAXT, MINB>;
   BASD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(batch * csize);
@@ -647,12 +693,22 @@ template <int G, int NF>
 static int launch_cluster(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims,
                           float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                           int dim_hi, int* rot_out) {
-  constexpr int GPC_MAX = 192 / G;                        // 192 threads: up to 255 registers each
+  int GPC_MAX = 192 / G;                                  // 192 threads: up to 255 registers each
   const int cap = (dims && dim_hi < n) ? dim_hi : n;
   const int groups = (cap + R - 1) / R;
   // 16-lane groups: portable clusters (<= 8 CTAs).  32-lane groups (rows up to 768 floats): 6 groups
   // per CTA, so 768 rows need the non-portable cluster size 16 (one such cluster per GPC).
   const int cmax = (G == 32) ? 16 : 8;
+  // while the whole launch still fits one wave, half as many groups per CTA on twice the CTAs shortens
+  // the step (three warps per SM instead of six: 16 x 384^2 eigenproblems 5.51 -> 5.36 ms)
+  if (G == 16) {
+    int c2 = 1;
+    while (c2 < cmax && c2 * (GPC_MAX / 2) < groups) c2 <<= 1;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (c2 * (GPC_MAX / 2) >= groups && (long)batch * c2 <= sms) GPC_MAX /= 2;
+  }
   int csize = 1;
   while (csize < cmax && csize * GPC_MAX < groups) csize <<= 1;
   if (csize * GPC_MAX < groups) return -100;
@@ -660,7 +716,7 @@ static int launch_cluster(float* Gm, int n, int m, int ld, long stride, int batc
   if (G == 16) gpc = (gpc + 1) & ~1;                      // whole warps
   const int threads = gpc * G;
   const size_t nslots = gpc + 1;
-  const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
+  const size_t dyn = (nslots * row_pitch<G, NF>() + 2 * nslots + 4) * sizeof(float);
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_cluster_kernel<G, NF>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   if (csize > 8)
@@ -692,7 +748,7 @@ static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;
   const size_t nslots = threads / G + 1;
-  const size_t dyn = (nslots * NF * G + 2 * nslots + 4) * sizeof(float);
+  const size_t dyn = (nslots * row_pitch<G, NF>() + 2 * nslots + 4) * sizeof(float);
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_kernel<G, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dyn));
   jacobi_rows_oe8_kernel<G, NF><<<batch, threads, dyn, st>>>(Gm, n, m, ld, stride, dims, tol, max_sweeps,
@@ -711,18 +767,8 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
   const int cap_n = (dims && !rows_only && dim_hi < n) ? dim_hi : n;
   const int cap_m = (dims && !rows_only && dim_hi < m) ? dim_hi : m;
   if (cap_n > 256 || cap_m > 256) return -100;          // 16 warps x 128 registers per CTA
-  // 32 lanes per group: twice the warps per SM for the same work, 72 registers
-  static const bool wide = getenv("BASD_JACOBI_OE8_G32") != nullptr;   // measured slower (25.1 vs 19.7 ms at C2): opt-in only
 #define BASD_OE8(NF) \
   return oe8::launch<16, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out, rows_only)
-#define BASD_OE8W(NF) \
-  return oe8::launch<32, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out, rows_only)
-  if (wide && cap_n > 64) {
-    if (cap_m <= 128) BASD_OE8W(4);
-    if (cap_m <= 160) BASD_OE8W(5);
-    if (cap_m <= 192) BASD_OE8W(6);
-    if (cap_m <= 224 && cap_n <= 224) BASD_OE8W(7);
-  }
   if (cap_m <= 64) BASD_OE8(4);
   if (cap_m <= 96) BASD_OE8(6);
   if (cap_m <= 128) BASD_OE8(8);
@@ -731,34 +777,25 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
   if (cap_m <= 208) BASD_OE8(13);
   if (cap_m <= 224) BASD_OE8(14);
   BASD_OE8(16);
-#undef BASD_OE8W
 #undef BASD_OE8
 }
 
-// Opt-in split of the small problems over 2 or 4 CTAs (see jacobi_rows_oe8_split_kernel): full problems
-// (dims == null) or square problems with a device-side active size inside [dim_lo, dim_hi] (the k x k
-// principal-angle SVDs: 48 problems leave two thirds of the SMs idle on the single-CTA kernel).
-// Returns -100 when the shape does not fit.
+// Split of the small problems over 4 CTAs (see jacobi_rows_oe8_split_kernel), for launches with few
+// problems: full problems (dims == null) or square problems with a device-side active size inside
+// [dim_lo, dim_hi].  Returns -100 when the shape does not fit.
 int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
                             int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
                             int dim_hi, int rows_only) {
-  const bool ro = rows_only && dims;
-  const int cap_n = (!ro && dims && dim_hi < n) ? dim_hi : n;
-  const int cap_m = (!ro && dims && dim_hi < m) ? dim_hi : m;
-  if (cap_n > 256 || cap_m > 208 || (csize != 2 && csize != 4)) return -100;
-#define BASD_OE8S2(NF, RO)                                                                                 \
-  return csize == 2 ? oe8::launch_split<NF, 224, 2, RO>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,     \
-                                                        sweeps_out, st, rot_out, csize, dim_lo, dim_hi)        \
-                    : oe8::launch_split<NF, 128, 3, RO>(G, n, m, ld, stride, batch, dims, tol, max_sweeps,     \
-                                                        sweeps_out, st, rot_out, csize, dim_lo, dim_hi)
-#define BASD_OE8S(NF)         \
-  if (ro) BASD_OE8S2(NF, true); \
-  BASD_OE8S2(NF, false)
-  if (cap_m <= 128) { BASD_OE8S(8); }
-  if (cap_m <= 192) { BASD_OE8S(12); }
+  const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
+  const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
+  if (cap_n > 256 || cap_m > 208 || csize != 4 || rows_only) return -100;
+#define BASD_OE8S(NF)                                                                                         \
+  return oe8::launch_split<NF, 128, 3>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, rot_out, \
+                                       csize, dim_lo, dim_hi)
+  if (cap_m <= 128) BASD_OE8S(8);
+  if (cap_m <= 192) BASD_OE8S(12);
   BASD_OE8S(13);
 #undef BASD_OE8S
-#undef BASD_OE8S2
 }
 
 // Cluster variant: up to 768 active rows; up to 384 active columns with 16-lane groups (portable
@@ -777,8 +814,6 @@ int launch_jacobi_oe8_cluster(float* G, int n, int m, int ld, long stride, int b
   if (cap_m <= 256) BASD_OE8C(16, 16);
   if (cap_m <= 320) BASD_OE8C(16, 20);
   if (cap_m <= 384) BASD_OE8C(16, 24);
-  static const bool wide = getenv("BASD_JACOBI_NO_OE8_WIDE") == nullptr;
-  if (!wide) return -100;
   if (cap_m <= 512) BASD_OE8C(32, 16);
   if (cap_m <= 640) BASD_OE8C(32, 20);
   BASD_OE8C(32, 24);

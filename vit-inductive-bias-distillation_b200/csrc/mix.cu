@@ -245,13 +245,13 @@ weight_grad_kernel(LayerPtrs layers, int E, const float* __restrict__ Z, int B, 
   }
 }
 
-// Opt-in experiment (BASD_WGRAD_ONEPASS=1, not yet measured): the same partial sums with the upstream
-// gradient read ONCE.  weight_grad_kernel above runs one block column per teacher layer, so every block
+// The same partial sums with the upstream gradient read ONCE (default for E <= 4; measured on B200 at C2:
+// 0.96 -> 0.59 ms).  weight_grad_kernel above runs one block column per teacher layer, so every block
 // column re-reads its slice of Z (E*B*N*D fp32, 616 MB at C2) -- ncu shows 2.4x the algorithmic DRAM
 // bytes.  Here a thread keeps its E x 8 values of Z in registers and walks LC teacher layers with them,
 // accumulating E x LC partial sums (48 registers for E = 4, LC = 12); grid = (slices, ceil(L / LC)).
-template <typename TIn, int EC, int LC>
-__global__ void __launch_bounds__(256)
+template <typename TIn, int EC, int LC, bool FAST>
+__global__ void __launch_bounds__(256, 2)
 weight_grad_onepass_kernel(LayerPtrs layers, int L, int E, const float* __restrict__ Z, int B, int n_src,
                            int n_dst, int D, float* __restrict__ partial) {
   __shared__ float red[8][EC * LC];
@@ -288,6 +288,36 @@ weight_grad_onepass_kernel(LayerPtrs layers, int L, int E, const float* __restri
 #pragma unroll
         for (int c = 0; c < 8; ++c) z[i][c] = 0.f;
       }
+    }
+    if (FAST && sizeof(TIn) == 2) {
+      // bf16 stack, no resampling: the 128-bit loads of UNR layers are issued before any is consumed and
+      // stay packed (4 registers each) until their turn
+      constexpr int UNR = (LC % 6 == 0) ? 6 : 4;
+#pragma unroll
+      for (int k0 = 0; k0 < LC; k0 += UNR) {
+        uint4 raw[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          raw[u] = __ldg(reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(layers.p[min(l0 + k0 + u, L - 1)]) + off_lo));
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (l0 + k0 + u < L) {
+            const uint32_t w4[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+            for (int i = 0; i < EC; ++i) {
+              float sum = acc[i][k0 + u];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                sum = fmaf(z[i][2 * c], __uint_as_float(w4[c] << 16), sum);
+                sum = fmaf(z[i][2 * c + 1], __uint_as_float(w4[c] & 0xffff0000u), sum);
+              }
+              acc[i][k0 + u] = sum;
+            }
+          }
+        }
+      }
+      continue;
     }
 #pragma unroll
     for (int k = 0; k < LC; ++k) {
@@ -347,7 +377,7 @@ weight_grad_onepass_kernel(LayerPtrs layers, int L, int E, const float* __restri
 __global__ void weight_grad_finish_kernel(const float* __restrict__ partial, int slices,
                                           const float* __restrict__ gw,
                                           const float* __restrict__ rows, int E, int L, int B,
-                                          int n_src, int n_dst, float gw_scale,
+                                          int n_rows, int n_dst, float gw_scale,
                                           const float* __restrict__ gw_scale_dev,
                                           float* __restrict__ d_weights) {
   __shared__ float red[32];
@@ -359,8 +389,8 @@ __global__ void weight_grad_finish_kernel(const float* __restrict__ partial, int
     const int b = idx / n_dst;
     int lo, hi;
     float f;
-    taps(n, n_src, n_dst, lo, hi, f);
-    const float* r = rows + ((long)l * B + b) * n_src;
+    taps(n, n_rows, n_dst, lo, hi, f);
+    const float* r = rows + ((long)l * B + b) * n_rows;
     const float v = r[lo] + f * (r[hi] - r[lo]);
     s = fmaf(gw[((long)i * B + b) * n_dst + n], v, s);
   }
@@ -403,8 +433,7 @@ extern "C" int basd_mix_interp(const void* const* teacher_layers, int L, int E, 
   const long total = (long)B * n_dst * (D >> 3);
   const unsigned grid = (unsigned)((total + 255) / 256);
   // six layers in flight when that divides the stack (12, 18, 24 layers), four otherwise
-  static const int unr_env = getenv("BASD_MIX_UNR") ? atoi(getenv("BASD_MIX_UNR")) : 0;
-  const bool six = unr_env ? (unr_env == 6) : (L % 6 == 0);
+  const bool six = L % 6 == 0;
 #define BASD_MIX(TI, TO, NE)                                                                      \
   do {                                                                                            \
     if (six)                                                                                      \
@@ -443,26 +472,31 @@ extern "C" int basd_mix_rows(const float* rows, const float* weights, int E, int
 
 extern "C" int basd_weight_grad_slices(void) { return 148 * 2; }
 
-// partial: (slices, L, E) scratch, d_weights: (E, L).
+// partial: (slices, L, E) scratch, d_weights: (E, L).  n_src: token count of the teacher layers,
+// n_rows: length of the importance rows (the attention map's own token count; it differs from n_src
+// when the caller hands over tokens that were already resampled, relational.py:29-32).
 extern "C" int basd_weight_grad(const void* const* teacher_layers, int L, int E, const float* Z,
                                 const float* gw, const float* rows, int in_dtype, int B, int n_src,
-                                int n_dst, int D, float gw_scale, const float* gw_scale_dev,
+                                int n_rows, int n_dst, int D, float gw_scale, const float* gw_scale_dev,
                                 float* partial, float* d_weights, void* stream) {
   if (E > MAX_E || (D & 7)) return -7;
   LayerPtrs lp;
   if (int rc = fill_layers(lp, teacher_layers, L)) return rc;
   const int slices = basd_weight_grad_slices();
-  static const bool onepass = getenv("BASD_WGRAD_ONEPASS") != nullptr;   // opt-in experiment, see the kernel
-  if (onepass && E <= 4) {
+  // E <= 4: one pass over the upstream gradient, 12 teacher layers per thread (0.96 -> 0.59 ms at C2 on
+  // B200, DRAM traffic 2.4x -> ~1x the algorithmic bytes); more extraction points take the per-layer grid
+  if (E <= 4) {
     constexpr int LC = 12;
     dim3 g1(slices, (L + LC - 1) / LC);
-    if (in_dtype == BASD_DTYPE_BF16)
-      weight_grad_onepass_kernel<__nv_bfloat16, 4, LC><<<g1, 256, 0, ST>>>(lp, L, E, Z, B, n_src, n_dst, D, partial);
+    if (in_dtype == BASD_DTYPE_BF16 && n_src == n_dst)
+      weight_grad_onepass_kernel<__nv_bfloat16, 4, LC, true><<<g1, 256, 0, ST>>>(lp, L, E, Z, B, n_src, n_dst, D, partial);
+    else if (in_dtype == BASD_DTYPE_BF16)
+      weight_grad_onepass_kernel<__nv_bfloat16, 4, LC, false><<<g1, 256, 0, ST>>>(lp, L, E, Z, B, n_src, n_dst, D, partial);
     else
-      weight_grad_onepass_kernel<float, 4, LC><<<g1, 256, 0, ST>>>(lp, L, E, Z, B, n_src, n_dst, D, partial);
+      weight_grad_onepass_kernel<float, 4, LC, false><<<g1, 256, 0, ST>>>(lp, L, E, Z, B, n_src, n_dst, D, partial);
     BASD_LAUNCH_CHECK();
     dim3 fg(L, E);
-    weight_grad_finish_kernel<<<fg, 256, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_src, n_dst, gw_scale,
+    weight_grad_finish_kernel<<<fg, 256, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_rows, n_dst, gw_scale,
                                                  gw_scale_dev, d_weights);
     BASD_LAUNCH_CHECK();
     return 0;
@@ -474,7 +508,7 @@ extern "C" int basd_weight_grad(const void* const* teacher_layers, int L, int E,
     weight_grad_kernel<float><<<grid, 256, 0, ST>>>(lp, E, Z, B, n_src, n_dst, D, partial);
   BASD_LAUNCH_CHECK();
   dim3 fgrid(L, E);
-  weight_grad_finish_kernel<<<fgrid, 256, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_src, n_dst,
+  weight_grad_finish_kernel<<<fgrid, 256, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_rows, n_dst,
                                                    gw_scale, gw_scale_dev, d_weights);
   BASD_LAUNCH_CHECK();
   return 0;

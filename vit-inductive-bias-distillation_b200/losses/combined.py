@@ -62,6 +62,7 @@ class BASDLoss(nn.Module):
             has_cls=self.teacher_has_cls_token, n_student=self.num_student_tokens)
         students = [student_intermediates[l] for l in self.token_layers]
         geo_loss = ProcrustesGeo.apply(weights, step, *students)                # :63-76
+        sel.last_state.sweeps["procrustes"] = step.procrustes.sweeps
         # UW-SO (reference :78-85): w_i = (1/L_i) / sum_j (1/L_j), weights detached.
         vals = torch.stack([ce_loss.detach().float(), geo_loss.detach()])
         if step.world > 1:       # weights from the global (concatenated-batch) losses

@@ -8,6 +8,7 @@ and ``forward`` signature.  The arithmetic runs in libbasd_b200.so (DESIGN.md §
 from __future__ import annotations
 
 import math
+import types
 
 import torch
 import torch.nn as nn
@@ -113,8 +114,7 @@ class GrassmannianLayerSelector(nn.Module):
             torch.full((num_extraction_points,), math.log(math.exp(1.0) - 1)))
         self.process_group = None
         self.sync_stats = True
-        self.last_state = None
-        self.last_step = None
+        self.last_state = None           # small diagnostics of the last step (ranks, edges, dist, weights, ...)
 
     @property
     def temperatures(self) -> torch.Tensor:
@@ -122,6 +122,9 @@ class GrassmannianLayerSelector(nn.Module):
 
     def _step(self, teacher_tokens, teacher_attns, has_cls, n_student) -> StepContext:
         keys = sorted(teacher_tokens.keys())
+        if set(teacher_attns.keys()) != set(keys):
+            raise ValueError(f"teacher token layers {keys} and attention maps "
+                             f"{sorted(teacher_attns.keys())} have different keys")
         world = world_size(self.process_group) if self.sync_stats else 1
         return StepContext(
             teachers=[teacher_tokens[k] for k in keys], attns=[teacher_attns[k] for k in keys],
@@ -138,8 +141,12 @@ class GrassmannianLayerSelector(nn.Module):
         step = self._step(all_teacher_tokens, all_teacher_attns, has_cls, n_student)
         weights = MixingWeights.apply(self.log_temperatures, step, *students)
         self.subspace_ranks._stage(sorted(all_teacher_tokens.keys()), step.selector.ranks)
-        self.last_state = step.selector
-        self.last_step = step
+        # keep only the small diagnostics alive between steps: the step context (contiguous teacher
+        # copies, Procrustes operators, selector factors: ~3 GB at C2) dies with the autograd graph
+        sel = step.selector
+        self.last_state = types.SimpleNamespace(
+            ranks=sel.ranks, edges=sel.edges, dist=sel.dist, weights=sel.weights, temps=sel.temps,
+            sweeps=dict(sel.sweeps))
         return weights, step
 
     def forward(self, student_tokens_per_layer, all_teacher_tokens, all_teacher_attns,
