@@ -42,6 +42,37 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, sm_max_mhz=1965.0, source="fallback")
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs local to GPU `index` BEFORE any pinned host buffer is allocated,
+    so that cudaHostAlloc places the staging pages on the GPU's own NUMA node (eight ranks streaming
+    1.1 GB per step each through a remote socket is what broke the end-to-end scaling in round 1).
+    Returns a short description for the JSON line; a no-op when sysfs has no answer."""
+    try:
+        prop = torch.cuda.get_device_properties(index)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(f"{base}/numa_node").read())
+        cpus = open(f"{base}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids & os.sched_getaffinity(0) or ids)
+        return {"numa_node": node, "cpus": cpus}
+    except Exception as exc:                                 # no sysfs entry, restricted cpuset, ...
+        return {"numa_node": None, "note": f"not bound ({type(exc).__name__})"}
+
+
+def measured_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that have a
+    byte model, from the committed `ncu --set full` captures (profiles/r2_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path))
+    return {}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons DURING the timed region through in-process NVML
     (a polling `nvidia-smi` subprocess perturbs the launch thread); falls back to one
@@ -143,8 +174,14 @@ def flop_model(work, ranks_mean):
     b, n, ds, dt, l, e = work.batch, work.n_student, work.d_student, work.d_teacher, work.teacher_layers, work.num_points
     m_s, m_t = b * work.n_student, b * work.n_teacher
     gram = 2.0 * m_t * dt * dt * l / 2 + 2.0 * m_s * ds * ds * e / 2     # symmetric token-space Grams
-    mix_bytes = (l * b * work.n_teacher * dt + e * b * n * dt) * 2.0
-    return dict(gram_flops=gram, mix_bytes=mix_bytes)
+    tok = 2.0 if work.token_dtype == torch.bfloat16 else 4.0
+    out_b = tok if work.n_teacher == n else 4.0                          # resampled tokens are written in fp32
+    mix_bytes = l * b * work.n_teacher * dt * tok + e * b * n * dt * out_b
+    # dL/dweights: the teacher stack once + the upstream gradient (E,B,N,D_t) fp32 once
+    wgrad_bytes = l * b * work.n_teacher * dt * tok + e * b * n * dt * 4.0
+    # pivoted Cholesky: n^3 / 3 multiply-adds per factorisation (left-looking dot products), 2 flops each
+    chol_flops = 2.0 * (2 * e * b * n ** 3 / 3.0 + (l + e) * ds ** 3 / 3.0)
+    return dict(gram_flops=gram, mix_bytes=mix_bytes, wgrad_bytes=wgrad_bytes, chol_flops=chol_flops)
 
 
 def roofline(work, mod, args5, pk, clocks):
@@ -155,6 +192,7 @@ def roofline(work, mod, args5, pk, clocks):
     one_step(mod, *args5)
     torch.cuda.synchronize()
     eng.jacobi_log = []
+    nat.gemm_flops = {}
     nat.start_timeline()
     one_step(mod, *args5)
     tl = nat.stop_timeline()
@@ -171,6 +209,7 @@ def roofline(work, mod, args5, pk, clocks):
     total = sum(v[0] for v in agg.values())
     table = sorted(((k, v[0], v[1]) for k, v in agg.items()), key=lambda x: -x[1])
     fm = flop_model(work, None)
+    gemm_flops = dict(nat.gemm_flops)
     sm_mhz = clocks.get("sm_mhz") or pk["sm_max_mhz"]
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     # Jacobi: algorithmic flops of the launches of this step = pair visits x one dot product (2m)
@@ -198,6 +237,15 @@ def roofline(work, mod, args5, pk, clocks):
                        peak=pk["bf16_sustained"] if name.endswith("tc") else fp32_peak, unit="TFLOP/s")
         elif name == "basd_mix_interp":
             rec.update(bound="hbm", achieved=fm["mix_bytes"] / (ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s")
+        elif name == "basd_weight_grad":
+            rec.update(bound="hbm", achieved=fm["wgrad_bytes"] / (ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s")
+        elif name == "basd_pivoted_cholesky" and work.d_student > work.n_student and work.d_teacher > work.n_student:
+            rec.update(bound="fp32", achieved=fm["chol_flops"] / (ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s")
+        elif name in gemm_flops:
+            # 3xTF32: three tensor-core MMAs per fp32-equivalent product; the roofline counts the fp32-equivalent
+            # flops against the measured dense bf16 rate / 2 (TF32 issues at half the bf16 rate) / 3
+            rec.update(bound="tensor", achieved=gemm_flops[name] / (ms * 1e-3) / 1e12,
+                       peak=pk["bf16_sustained"] / 6.0, unit="TFLOP/s(fp32-equivalent, 3xTF32)")
         if "achieved" in rec:
             rec["frac"] = rec["achieved"] / rec["peak"]
         records.append(rec)
@@ -211,9 +259,11 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)      # before the first pinned allocation
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=300))
+    parity = dp_parity(args, rank, world, device) if world > 1 and not args.no_dp_parity else None
     work = syn.scaled(syn.WORKLOADS[args.workload], args.batch)
     mod = build_module(work, device)
     logits, targets, st, te, at = make_inputs(args, work, rank, device)
@@ -357,8 +407,16 @@ def run_b200(args):
         "step_ms": [round(x, 2) for x in per_step],
         "clocks": clocks, "gpu_launches": launches // max(1, args.steps),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": 4, "ms_per_step": round(float(t.item()), 3)},
+                "d2h_bytes_per_step": 4, "ms_per_step": round(float(t.item()), 3),
+                "h2d_gb_per_s_per_gpu": round(h2d / (float(t.item()) * 1e-3) / 1e9, 2),
+                "staging": numa,
+                "inputs": ("student + teacher tokens in full; of every teacher attention map only the CLS query "
+                           "row (B,H,N+1) is staged on the host and copied -- the loss reads nothing else "
+                           "(SURVEY 8-f1 capture contract, not the reference's full-map input)"
+                           if work.has_cls else "student + teacher tokens and attention maps in full")},
     }
+    if parity is not None:
+        line["dp_parity"] = parity
     # every rank runs the profiled step (the loss all-reduces inside); only rank 0 reports
     records, total, fp32_peak = roofline(work, mod, args5, pk, clocks)
     if rank == 0:
@@ -366,15 +424,18 @@ def run_b200(args):
         line["kernel_ms_total"] = round(total, 3)
         # the dominant kernel that has a byte / flop model (records are sorted by time)
         top = next((r for r in records if "achieved" in r), None)
+        traffic = measured_traffic() if args.workload == "c2" and args.batch == 256 else {}
         if top:
             line["roofline"] = {"kernel": top["kernel"], "bound": top["bound"], "achieved": round(top["achieved"], 2),
                                 "peak": round(top["peak"], 2), "unit": top["unit"], "frac": round(top["frac"], 4),
-                                "traffic": None, "peak_source": pk["source"]}
-        # one entry per kernel family the north star asks evidence for: tensor pipe (Gram), FP32 pipe
-        # (Jacobi), HBM (mix / resample); the fp32 peak uses the SM clock observed during the run
+                                "traffic": traffic.get(top["kernel"]), "peak_source": pk["source"]}
+        # one entry per kernel family the north star asks evidence for: tensor pipe (Gram, 3xTF32 GEMMs), FP32
+        # pipe (Jacobi, Cholesky), HBM (mix / resample, weight gradient); the fp32 peak uses the SM clock
+        # observed during the run; `traffic` = DRAM bytes per launch from the committed ncu capture
         line["rooflines"] = [{"kernel": r["kernel"], "bound": r["bound"], "achieved": round(r["achieved"], 2),
                               "peak": round(r["peak"], 2), "unit": r["unit"], "frac": round(r["frac"], 4),
-                              "ms": r["ms"]} for r in records if "achieved" in r]
+                              "ms": r["ms"], "launches": r.get("launches", 1),
+                              "traffic": traffic.get(r["kernel"])} for r in records if "achieved" in r]
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, sample_batch=args.cpu_batch, steps=1)
         print(json.dumps(line))
@@ -382,36 +443,43 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ data-parallel parity
+def dp_parity(args, rank, world, device):
+    """Before any timing at N > 1: one small-batch data-parallel step of the timed workload's shape,
+    checked on rank 0 against the CPU oracle evaluated on the CONCATENATED batch (the
+    parity target of the all-reduced statistics).  Returns the record printed as `dp_parity`."""
+    from tests import _cases as cs            # test infrastructure: the oracle is the checker here
+    local_batch = 4
+    temps = [0.3, 0.541, 0.8, 1.2]
+    work = cs.workload(args.workload, local_batch)
+    temps = temps[:work.num_points] + [0.6] * max(0, work.num_points - len(temps))
+    inputs = syn.make_inputs(work, seed=6, batch_offset=rank * local_batch)
+    got = cs.run_cuda(work, inputs, temps, device=device)
+    glob = float(got["module"].last["global_loss"])
+    rec = None
+    if rank == 0:
+        full = cs.workload(args.workload, local_batch * world)
+        ref = cs.run_oracle(full, syn.make_inputs(full, seed=6), temps)
+        cos = min(cs.cosine(got["grad_students"][l] / world, ref["grad_students"][l][:local_batch])
+                  for l in ref["layers"])
+        rec = {"local_batch": local_batch, "world": world, "reference": "CPU oracle on the concatenated batch",
+               "loss_rel": abs(glob - float(ref["loss"])) / abs(float(ref["loss"])),
+               "weights_max_abs": float((got["weights"] - ref["weights"]).abs().max()),
+               "ranks_equal": got["ranks"] == ref["ranks"],
+               "grad_cos_min": cos,
+               "log_temp_grad_cos": cs.cosine(got["grad_log_temps"], ref["grad_log_temps"])}
+        rec["ok"] = bool(rec["loss_rel"] < 1e-3 and rec["weights_max_abs"] < 1e-4 and cos > 0.999
+                         and rec["log_temp_grad_cos"] > 0.999)
+    del got
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return rec
+
+
 # ------------------------------------------------------------------ CPU arms
-def cpu_baseline(args, sample_batch, steps):
-    """The reference algorithm (oracle port: same torch.linalg calls as the reference) on the
-    host cores, on a bounded sample of the workload."""
+def cpu_setup(args, batch):
     torch.set_num_threads(os.cpu_count())
-    work = syn.scaled(syn.WORKLOADS[args.workload], sample_batch)
-    mod = build_module(work, "cpu", impl="reference")
-    logits, targets, st, te, at = make_inputs(args, work, 0, "cpu")
-    st = {k: v.float().requires_grad_(True) for k, v in st.items()}
-    te = {k: v.float() for k, v in te.items()}
-    logits.requires_grad_(True)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        for v in st.values():
-            v.grad = None
-        loss = mod(logits, targets, st, te, at)
-        loss.backward()
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": round(sample_batch / dt, 3), "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "port", "sample": f"{steps} step(s) of {work.name} (batch {sample_batch} of the "
-            f"workload's {args.batch}; the reference scales ~linearly in batch), fp32, autocast off",
-            "seconds_per_step": round(dt, 3)}
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    torch.set_num_threads(os.cpu_count())
-    work = syn.scaled(syn.WORKLOADS[args.workload], args.cpu_batch)
+    work = syn.scaled(syn.WORKLOADS[args.workload], batch)
     mod = build_module(work, "cpu", impl="reference")
     logits, targets, st, te, at = make_inputs(args, work, 0, "cpu")
     st = {k: v.float().requires_grad_(True) for k, v in st.items()}
@@ -424,8 +492,38 @@ def run_reference(args):
         loss = mod(logits, targets, st, te, at)
         loss.backward()
 
-    steps, warm = min(args.steps, 3), min(args.warmup, 1)
-    for _ in range(warm):
+    return work, step
+
+
+def cpu_baseline(args, sample_batch, steps):
+    """The reference algorithm (oracle port: same torch.linalg calls as the reference) on the
+    host cores, on a bounded sample of the workload."""
+    work, step = cpu_setup(args, sample_batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(sample_batch / dt, 3), "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port", "measured_batch": sample_batch,
+            "sample": f"{steps} step(s) of {work.name}: batch {sample_batch} of the workload's {args.batch}, "
+            "fp32, autocast off (bf16 tokens upcast exactly)", "seconds_per_step": round(dt, 3)}
+
+
+def run_reference(args):
+    """The reference's algorithm on the host cores (oracle port; the Python reference itself cannot travel
+    to the GPU box).  `config.batch_per_gpu` is the batch actually run: a bounded sample of the workload,
+    sized so that K + W steps end within a few minutes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    work, step = cpu_setup(args, args.cpu_batch)
+    budget_s = 240.0
+    t0 = time.perf_counter()
+    step()                                            # first warm-up step doubles as the time probe
+    probe = time.perf_counter() - t0
+    warm = max(1, min(args.warmup, int(0.2 * budget_s / probe)))
+    steps = max(1, min(args.steps, int(0.8 * budget_s / probe)))
+    for _ in range(warm - 1):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -438,15 +536,19 @@ def run_reference(args):
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
         "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": data_label(args),
-        "config": {"workload": full.name, "batch_per_gpu": full.batch, "student_tokens": full.n_student,
+        "config": {"workload": full.name, "batch_per_gpu": args.cpu_batch, "workload_batch": full.batch,
+                   "student_tokens": full.n_student,
                    "teacher_tokens": full.n_teacher, "student_dim": full.d_student,
                    "teacher_dim": full.d_teacher, "teacher_layers": full.teacher_layers,
                    "token_dtype": "float32 (bf16 tokens upcast: the reference cannot take bf16)",
                    "features": args.features,
                    "parallelism": "cpu"},
+        "measured_batch": args.cpu_batch,
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{steps} step(s) at batch {args.cpu_batch} of the workload's {args.batch} "
-                                   "(bounded sample; samples/s is ~flat in batch)"},
+                         "measured_batch": args.cpu_batch,
+                         "sample": f"{steps} step(s) (+{warm} warm-up) at batch {args.cpu_batch}: a bounded sample "
+                                   f"of the workload's batch {args.batch}; requested steps/warm-up "
+                                   f"{args.steps}/{args.warmup}, cut to a {int(budget_s)} s budget if needed"},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -460,8 +562,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(syn.WORKLOADS))
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dp-parity", action="store_true")
     ap.add_argument("--features", default="backbone", choices=["backbone", "spectral"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -141,6 +141,13 @@ int basd_omega_accumulate(const float* block, const float* lam_s, const int* ran
                           int L, float* omega, void* stream);
 int basd_symmetrize_add(const float* in, int D, float* out, int batch, void* stream);
 
+/* Null-space completion for rank-deficient student Grams (fewer token rows than dimensions, the regime of
+ * layer_selector.py:14-15): P = I - sym(vtv) with vtv = V_r^T V_r; after basd_pivoted_cholesky(P) rows
+ * 0..rank_P-1 of its factor are an orthonormal basis of the complement and are written into the zero rows
+ * D-rank_P..D-1 of Vt -- what the (I - V V^T) term of the thin-SVD backward (layer_selector.py:92) needs. */
+int basd_projector_complement(const float* vtv, int D, float* P, int batch, void* stream);
+int basd_place_complement(float* Vt, const float* LT, const int* rank_p, int D, int batch, void* stream);
+
 /* ---- HBM-bound mixing (mix.cu) ------------------------------------------------------ */
 
 /* attention map (B,H,q_rows,side) -> importance row (B, n_tok): CLS row mean over heads, or
@@ -155,6 +162,13 @@ int basd_attn_rows(const void* attn, int dtype, int B, int H, int side, int q_ro
 int basd_mix_interp(const void* const* teacher_layers, int L, int E, const float* weights,
                     int in_dtype, int B, int n_src, int n_dst, int D, void* out, int out_dtype,
                     void* stream);
+
+/* Flat layer mix out[i][x] = sum_l weights[i,l] * layer_l[x] over numel elements (any tensor shape), all E
+ * outputs in one pass: the reference-shaped outputs of GrassmannianLayerSelector.forward -- mixed full
+ * attention maps (layer_selector.py:112).  out: (E, numel) in the layers' dtype; layer pointers 16-byte
+ * aligned. */
+int basd_mix_flat(const void* const* layers, int L, int E, const float* weights, int dtype, long numel,
+                  void* out, void* stream);
 
 /* mixed + resampled + normalised token importance.   (layer_selector.py:112, relational.py:29-34) */
 int basd_mix_rows(const float* rows, const float* weights, int E, int L, int B, int n_src,

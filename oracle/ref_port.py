@@ -81,9 +81,14 @@ def extraction_layers(student_depth: int, num_points: int) -> list[int]:
 # a4-a6  selector                      reference: src/losses/layer_selector.py:69-152
 # --------------------------------------------------------------------------------------
 def selector_forward(student_tokens, teacher_tokens, teacher_attns, layers,
-                     proj_s, proj_t, log_temps):
+                     proj_s, proj_t, log_temps, ranks_override=None):
     """Returns mixed tokens/attn per student layer plus the diagnostics the parity tests
-    compare (ranks, distances, mixing weights, principal-angle cosines)."""
+    compare (ranks, distances, mixing weights, principal-angle cosines).
+
+    `ranks_override` (test hook, not in the reference): evaluate everything downstream of the
+    Marchenko-Pastur decision at the given ranks.  The rank is a discontinuous integer; when an
+    eigenvalue sits within 1e-4 of the threshold the kernels may land on the other side of it, and
+    the parity tests then compare against the reference algorithm run AT THE KERNEL'S RANK."""
     t_keys = sorted(teacher_tokens.keys())                # :123
     d_s = proj_s.shape[0]
     d_t = teacher_tokens[t_keys[0]].shape[2]
@@ -93,6 +98,8 @@ def selector_forward(student_tokens, teacher_tokens, teacher_attns, layers,
         for key in t_keys:
             z = teacher_tokens[key].reshape(-1, d_t) @ proj_t.T
             ranks[key] = min(mp_rank(z), d_s - 1)
+    if ranks_override is not None:
+        ranks = {key: int(ranks_override[j]) for j, key in enumerate(t_keys)}
 
     tok_stack = torch.stack([teacher_tokens[k] for k in t_keys])       # :128
     att_stack = torch.stack([teacher_attns[k] for k in t_keys])        # :129
@@ -183,11 +190,12 @@ def uwso(values: list[torch.Tensor]) -> torch.Tensor:
 
 def basd_forward(logits, targets, student_tokens, teacher_tokens, teacher_attns, *,
                  layers, proj_s, proj_t, log_temps, n_student_tokens, has_cls,
-                 criterion):
+                 criterion, ranks_override=None):
     """Full loss. Returns (loss, details)."""
     ce = criterion(logits, targets)                       # :56
     mixed_tok, mixed_att, diag = selector_forward(        # :58-61
-        student_tokens, teacher_tokens, teacher_attns, layers, proj_s, proj_t, log_temps)
+        student_tokens, teacher_tokens, teacher_attns, layers, proj_s, proj_t, log_temps,
+        ranks_override=ranks_override)
     geo_terms = []
     for layer in layers:                                  # :63-75
         aligned = align_tokens(mixed_tok[layer], n_student_tokens)

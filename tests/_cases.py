@@ -38,7 +38,7 @@ def criterion(work):
     return torch.nn.CrossEntropyLoss(label_smoothing=1.0 / work.num_classes)
 
 
-def run_oracle(work, inputs, log_temps=None):
+def run_oracle(work, inputs, log_temps=None, ranks_override=None):
     """fp32 oracle forward+backward on CPU (bf16 tokens upcast exactly). Returns dict."""
     logits, targets, st, te, at = inputs
     proj_s, proj_t, logt = selector_state(work)
@@ -52,7 +52,8 @@ def run_oracle(work, inputs, log_temps=None):
     layers = rp.extraction_layers(work.student_depth, work.num_points)
     loss, diag = rp.basd_forward(lg, targets.cpu(), st32, te32, at32, layers=layers, proj_s=proj_s,
                                  proj_t=proj_t, log_temps=logt, n_student_tokens=work.n_student,
-                                 has_cls=work.has_cls, criterion=criterion(work))
+                                 has_cls=work.has_cls, criterion=criterion(work),
+                                 ranks_override=ranks_override)
     loss.backward()
     return dict(loss=loss.detach(), ce=diag.ce, geo=diag.geo, geo_terms=diag.geo_terms,
                 ranks=[diag.ranks[k] for k in sorted(diag.ranks)],

@@ -14,7 +14,7 @@ import torch
 from oracle import ref_port as rp
 from basd_b200 import backbone_features as bb
 from tests import _cases as cs
-from tests.test_loss_parity_gpu import COS_TOL, LOSS_TOL, W_TOL, _ranks_ok
+from tests.test_loss_parity_gpu import COS_TOL, LOSS_TOL, W_TOL, _check_selector_at_kernel_rank, _ranks_ok
 
 pytestmark = pytest.mark.gpu
 
@@ -50,6 +50,8 @@ def test_random_init_backbones_against_live_oracle(key, student, teacher, batch,
     assert _ranks_ok(got["ranks"], ref["ranks"], got["module"])
     if got["ranks"] == ref["ranks"]:
         assert (got["weights"] - ref["weights"]).abs().max() < W_TOL
+    else:
+        _check_selector_at_kernel_rank(work, inputs, None, got)
     assert abs(float(got["geo"]) - float(ref["geo"])) / abs(float(ref["geo"])) < LOSS_TOL
     assert abs(float(got["loss"]) - float(ref["loss"])) / abs(float(ref["loss"])) < LOSS_TOL
     for layer in ref["layers"]:

@@ -113,3 +113,32 @@ def test_c3_full_size_single_teacher_layer_weights_are_one():
     assert set(mod.layer_selector.subspace_ranks.keys()) == {0}
     for v in st.values():
         assert torch.isfinite(v.grad.float()).all() and float(v.grad.float().norm()) > 0
+
+
+def test_c2_full_size_against_the_oracle():
+    """ONE direct comparison at BASELINE's full size (C2, B = 256, bf16 tokens): the CPU oracle's
+    forward + backward on the same inputs (tens of seconds on the GPU box's host cores) against the CUDA
+    path, at the north-star tolerances.  Everything else at this size is pinned by the invariants above."""
+    from tests.test_loss_parity_gpu import COS_TOL, LOSS_TOL, W_TOL, _check_selector_at_kernel_rank, _ranks_ok
+    work = _c2()
+    temps = [0.3, 0.6, 0.9, 1.2]
+    dev_inputs = syn.make_inputs_fast(work, seed=7, device=DEV)
+    inputs = tuple(x.cpu() if not isinstance(x, dict) else {k: v.cpu() for k, v in x.items()} for x in dev_inputs)
+    del dev_inputs
+    got = cs.run_cuda(work, inputs, temps)
+    torch.cuda.empty_cache()
+    ref = cs.run_oracle(work, inputs, temps)
+    print("c2 b256 loss", float(got["loss"]), float(ref["loss"]), "geo", float(got["geo"]), float(ref["geo"]),
+          "ranks", got["ranks"], ref["ranks"])
+    assert _ranks_ok(got["ranks"], ref["ranks"], got["module"])
+    if got["ranks"] == ref["ranks"]:
+        assert (got["weights"] - ref["weights"]).abs().max() < W_TOL
+        assert cs.cosine(got["grad_log_temps"], ref["grad_log_temps"]) > COS_TOL
+    else:
+        _check_selector_at_kernel_rank(work, inputs, temps, got)
+    assert abs(float(got["geo"]) - float(ref["geo"])) / abs(float(ref["geo"])) < LOSS_TOL
+    assert abs(float(got["loss"]) - float(ref["loss"])) / abs(float(ref["loss"])) < LOSS_TOL
+    for layer in ref["layers"]:
+        c = cs.cosine(got["grad_students"][layer], ref["grad_students"][layer])
+        print("  layer", layer, "grad cosine", c)
+        assert c > COS_TOL

@@ -1,14 +1,13 @@
 """C4 (DeiT-B <- ViT-L/16: D_s = 768, D_t = 1024, 24 teacher layers mixed) through the CUDA path
 against the live oracle at a batch the oracle finishes in seconds.  This is the only parity case
 that reaches the 768-wide selector kernels (16-CTA cluster Jacobi and Cholesky, the k x k SVD size
-window) -- the other workloads stop at 384.  The file sorts last on purpose: it was added after
-the round's GPU budget was spent, so its first run is the driver's."""
+window) -- the other workloads stop at 384."""
 import pytest
 import torch
 
 import basd_b200.synthetic as syn
 from tests import _cases as cs
-from tests.test_loss_parity_gpu import COS_TOL, LOSS_TOL, W_TOL, _ranks_ok
+from tests.test_loss_parity_gpu import COS_TOL, LOSS_TOL, W_TOL, _check_selector_at_kernel_rank, _ranks_ok
 
 pytestmark = pytest.mark.gpu
 
@@ -24,6 +23,8 @@ def test_c4_against_live_oracle():
     ranks_equal = got["ranks"] == ref["ranks"]
     if ranks_equal:
         assert (got["weights"] - ref["weights"]).abs().max() < W_TOL
+    else:
+        _check_selector_at_kernel_rank(work, inputs, None, got)
     assert abs(float(got["geo"]) - float(ref["geo"])) / abs(float(ref["geo"])) < LOSS_TOL
     assert abs(float(got["loss"]) - float(ref["loss"])) / abs(float(ref["loss"])) < LOSS_TOL
     for layer in ref["layers"]:
@@ -60,5 +61,12 @@ def test_selector_forward_returns_the_reference_shaped_dicts():
         assert mixed_tok[layer].shape == te[keys[0]].shape and mixed_att[layer].shape == at[keys[0]].shape
         assert (mixed_tok[layer].float().cpu() - want_tok).abs().max() < 1e-3 * want_tok.abs().max()
         assert (mixed_att[layer].float().cpu() - want_att).abs().max() < 1e-3 * want_att.abs().max()
+    # the importance-row form of the mixed attention: what relational.py:22-34 reduces the mixed map to
+    weights, step = sel.mixing_weights(st_d, te_d, at_d, mod.token_layers, has_cls=True)
+    rows = sel.mixed_importance(weights, step).cpu()
+    for i, layer in enumerate(mod.token_layers):
+        want = (ref["weights"][i].view(-1, 1, 1, 1, 1) * att).sum(0)[:, :, 0, 1:].mean(1)
+        want = want / want.sum(-1, keepdim=True)
+        assert (rows[i] - want).abs().max() < 1e-5
     assert [sel.subspace_ranks[k] for k in keys] == ref["ranks"] or _ranks_ok(
         [sel.subspace_ranks[k] for k in keys], ref["ranks"], mod)

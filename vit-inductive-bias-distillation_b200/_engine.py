@@ -56,6 +56,21 @@ def _f32(*shape, device):
     return torch.empty(*shape, dtype=torch.float32, device=device)
 
 
+def _pad4(x: int) -> int:
+    return (x + 3) // 4 * 4
+
+
+def _mat(p: int, rows: int, cols: int, device):
+    """(p, rows, pitch) fp32 with the pitch rounded up to a multiple of four floats: the factor
+    kernels read rows in 128-bit pieces, so a token count like 49, 225 or 577 needs padded rows.
+    The pad columns are zero and stay zero (rotations and products of zeros); the logical width is
+    passed to every kernel next to the pitch."""
+    pitch = _pad4(cols)
+    if pitch == cols:
+        return torch.empty(p, rows, cols, dtype=torch.float32, device=device)
+    return torch.zeros(p, rows, pitch, dtype=torch.float32, device=device)
+
+
 # ---------------------------------------------------------------------------- op wrappers
 # the Procrustes products run on the tensor cores (3xTF32, gemm_tc3.cu) unless this is set
 # (A/B measurements and the SIMT-vs-tensor parity test)
@@ -115,8 +130,10 @@ def token_gram(tokens: torch.Tensor, gram: torch.Tensor, colsum: torch.Tensor):
 
 
 def pivoted_cholesky(k, lt, rel_tol, dims=None, rank_out=None):
-    batch, n, _ = k.shape
-    call("basd_pivoted_cholesky", ptr(k), n, n, n * n, ptr(lt), n, n * n, batch, rel_tol,
+    """k, lt: (batch, n, pitch) with pitch >= n (see _mat)."""
+    batch, n, ldk = k.shape
+    ldl = lt.shape[2]
+    call("basd_pivoted_cholesky", ptr(k), n, ldk, n * ldk, ptr(lt), ldl, n * ldl, batch, rel_tol,
          ptr(rank_out), ptr(dims), stream())
 
 
@@ -125,10 +142,12 @@ def pivoted_cholesky(k, lt, rel_tol, dims=None, rank_out=None):
 jacobi_log = None
 
 
-def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi", tol=None, row_dims=None):
+def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi", tol=None, row_dims=None, cols=None):
     """dims: active leading size of square problems (rows and columns); row_dims: number of
-    leading non-zero rows (rank of the factor the rows come from), all columns active."""
-    batch, n, m = g.shape
+    leading non-zero rows (rank of the factor the rows come from), all columns active.
+    cols: logical row length when the rows are padded (g.shape[2] is the pitch)."""
+    batch, n, ld = g.shape
+    m = ld if cols is None else cols
     tol = JACOBI_TOL if tol is None else tol
     if row_dims is not None and dims is None:
         rot = None
@@ -136,23 +155,25 @@ def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi", tol=None, row_dims=
             sweeps_out = sweeps_out if sweeps_out is not None else torch.zeros(batch, dtype=torch.int32, device=g.device)
             rot = torch.zeros(batch, dtype=torch.int32, device=g.device)
             jacobi_log.append((tag, n, m, None, sweeps_out, rot, row_dims))
-        call("basd_jacobi_rows_ranked", ptr(g), n, m, m, n * m, batch, ptr(row_dims), tol, JACOBI_SWEEPS,
+        call("basd_jacobi_rows_ranked", ptr(g), n, m, ld, n * ld, batch, ptr(row_dims), tol, JACOBI_SWEEPS,
              ptr(sweeps_out), ptr(rot), stream())
         return
     if jacobi_log is not None:
         sweeps_out = sweeps_out if sweeps_out is not None else torch.zeros(batch, dtype=torch.int32, device=g.device)
         rot = torch.zeros(batch, dtype=torch.int32, device=g.device)
-        call("basd_jacobi_rows_counted", ptr(g), n, m, m, n * m, batch, ptr(dims), tol,
+        call("basd_jacobi_rows_counted", ptr(g), n, m, ld, n * ld, batch, ptr(dims), tol,
              JACOBI_SWEEPS, ptr(sweeps_out), ptr(rot), stream())
         jacobi_log.append((tag, n, m, dims, sweeps_out, rot, None))
         return
-    call("basd_jacobi_rows", ptr(g), n, m, m, n * m, batch, ptr(dims), tol, JACOBI_SWEEPS,
+    call("basd_jacobi_rows", ptr(g), n, m, ld, n * ld, batch, ptr(dims), tol, JACOBI_SWEEPS,
          ptr(sweeps_out), stream())
 
 
-def rows_normalize(g, out, vals, *, sort, square, rel_floor, dims=None):
-    batch, n, m = g.shape
-    call("basd_rows_normalize", ptr(g), n, m, m, n * m, ptr(out), m, n * m, ptr(vals), batch,
+def rows_normalize(g, out, vals, *, sort, square, rel_floor, dims=None, cols=None):
+    batch, n, ld = g.shape
+    m = ld if cols is None else cols
+    ldo = out.shape[2]
+    call("basd_rows_normalize", ptr(g), n, m, ld, n * ld, ptr(out), ldo, n * ldo, ptr(vals), batch,
          int(sort), int(square), rel_floor, ptr(dims), stream())
 
 
@@ -174,6 +195,21 @@ def sym_eig(kmats: torch.Tensor):
     lam = _f32(batch, d, device=dev)
     call("basd_rowdot", ptr(kv), d, d * d, ptr(vt), d, d * d, d, d, batch, ptr(lam), stream())
     return lam, vt
+
+
+def complete_null_space(vt: torch.Tensor):
+    """In place: the zero rows sym_eig leaves beyond the rank of a deficient Gram become an orthonormal
+    basis of its null space (selector.cu: projector + pivoted Cholesky).  Needed only when there are
+    fewer token rows than dimensions; the thin-SVD backward's (I - V V^T) term lives there."""
+    batch, d, _ = vt.shape
+    dev = vt.device
+    vtv = _f32(batch, d, d, device=dev)
+    sgemm(1, 0, d, d, d, vt, d, d * d, vt, d, d * d, vtv, d, d * d, batch)
+    proj = _f32(batch, d, d, device=dev)
+    call("basd_projector_complement", ptr(vtv), d, ptr(proj), batch, stream())
+    rank_p = torch.empty(batch, dtype=torch.int32, device=dev)
+    pivoted_cholesky(proj, vtv, 1e-3, rank_out=rank_p)      # projector eigenvalues are 0 or 1
+    call("basd_place_complement", ptr(vt), ptr(vtv), ptr(rank_p), d, batch, stream())
 
 
 def sharded_sym_eig(kmats: torch.Tensor, group, world: int, solver=None):
@@ -347,6 +383,8 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     lam, vt = sharded_sym_eig(kall, group, world)
     lam_t, lam_s = lam[:l], lam[l:]
     vt_t, vt_s = vt[:l], vt[l:]
+    if rows_s < d_s:          # rank-deficient student Grams: complete the eigenvector basis
+        complete_null_space(vt_s)
     y_t = _f32(l, d_s, device=dev)                        # y = V^T c_hat per teacher layer
     sgemm(0, 0, d_s, 1, d_s, vt_t, d_s, d_s * d_s, chat_t, 1, d_s, y_t, 1, d_s, l)
     ranks = torch.empty(l, dtype=torch.int32, device=dev)
@@ -419,13 +457,15 @@ class _Side:
                  self.p, ptr(self.diag), stream())
             self.fac, self.ld = tok, self.d              # stored as F (N x r)
         else:
-            k = _f32(self.p, n, n, device=dev)
-            sgemm(0, 1, n, n, self.d, tok, self.d, n * self.d, tok, self.d, n * self.d, k, n, n * n, self.p, tc=True)
-            call("basd_extract_diag", ptr(k), n, n, n * n, self.p, ptr(self.diag), stream())
-            self.fac = _f32(self.p, n, n, device=dev)    # stored as F^T (r x N)
+            ldn = _pad4(n)
+            k = _mat(self.p, n, n, dev)
+            sgemm(0, 1, n, n, self.d, tok, self.d, n * self.d, tok, self.d, n * self.d, k, ldn, n * ldn, self.p,
+                  tc=True)
+            call("basd_extract_diag", ptr(k), n, ldn, n * ldn, self.p, ptr(self.diag), stream())
+            self.fac = _mat(self.p, n, n, dev)           # stored as F^T (r x N)
             self.rank = torch.empty(self.p, dtype=torch.int32, device=dev)
             pivoted_cholesky(k, self.fac, CHOL_TOL, rank_out=self.rank)
-            self.ld = n
+            self.ld = ldn
         self.stride = self.fac.shape[1] * self.fac.shape[2]
 
     # operand descriptors for sgemm: (transpose flag, tensor, ld, stride)
@@ -491,19 +531,19 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
         swap = True
     sq, sp = (side_s, side_t) if swap else (side_t, side_s)
     rq, rp = sq.r, sp.r
-    g = _f32(p, rq, rp, device=dev)
+    lrq, lrp, ldn = _pad4(rq), _pad4(rp), _pad4(n)        # pitches (a Gram side's width is the token count)
+    g = _mat(p, rq, rp, dev)
     ta, fa_, lda, sa = sq.ft_left()
     tb, fb_, ldb, sb = sp.f_right()
-    sgemm(ta, tb, rq, rp, n, fa_, lda, sa, fb_, ldb, sb, g, rp, rq * rp, p, tc=True)       # G = F_q^T F_p
-    g0 = _f32(p, rq, rp, device=dev)
-    g0.copy_(g)
+    sgemm(ta, tb, rq, rp, n, fa_, lda, sa, fb_, ldb, sb, g, lrp, rq * lrp, p, tc=True)     # G = F_q^T F_p
+    g0 = g.clone()
     sweeps = torch.zeros(p, dtype=torch.int32, device=dev)
     # rows -> sigma_j p_j^T; rows of G beyond the rank of a Gram-side F_q are exact zeros
-    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes", tol=PROC_JACOBI_TOL, row_dims=sq.rank)
-    rows_normalize(g, g, None, sort=False, square=False, rel_floor=ROW_FLOOR)
+    jacobi_rows(g, sweeps_out=sweeps, tag="procrustes", tol=PROC_JACOBI_TOL, row_dims=sq.rank, cols=rp)
+    rows_normalize(g, g, None, sort=False, square=False, rel_floor=ROW_FLOOR, cols=rp)
     pt = g                                                                # (rq, rp) unit rows
-    rows2 = _f32(p, rq, rq, device=dev)
-    sgemm(0, 1, rq, rq, rp, pt, rp, rq * rp, g0, rp, rq * rp, rows2, rq, rq * rq, p, tc=True)  # P^T G^T = S Q^T
+    rows2 = _mat(p, rq, rq, dev)
+    sgemm(0, 1, rq, rq, rp, pt, lrp, rq * lrp, g0, lrp, rq * lrp, rows2, lrq, rq * lrq, p, tc=True)  # P^T G^T = S Q^T
     del g0
     # scaling exponents (in halves) of the own-vector rows, see basd_procrustes_rows_finish
     e_s = -1 if not side_t.direct else 0
@@ -520,42 +560,42 @@ def procrustes_forward(students, teachers, stats: Stats, weights, n_student, wit
     sig = _f32(p, rq, device=dev)
     pic = _f32(p, rq, device=dev)
     nuc = _f32(p, device=dev)
-    call("basd_procrustes_rows_finish", ptr(rows2), rq, rq, rq * rq, ptr(pt), rp, rp, rq * rp, p,
+    call("basd_procrustes_rows_finish", ptr(rows2), rq, lrq, rq * lrq, ptr(pt), rp, lrp, rq * lrp, p,
          floor, floor_q, eq, ep, ptr(sig), ptr(nuc), ptr(pic), stream())
     f = _f32(p, device=dev)
     m_a = m_b = g_a = g_b = gw = None
     if with_grad:
-        img_q = _f32(p, rq, n, device=dev)                # rows (F_q q_j)^T (scaled)
-        img_p = _f32(p, rq, n, device=dev)                # rows (F_p p_j)^T (scaled)
+        img_q = _mat(p, rq, n, dev)                       # rows (F_q q_j)^T (scaled)
+        img_p = _mat(p, rq, n, dev)                       # rows (F_p p_j)^T (scaled)
         tb, fb_, ldb, sb = sq.ft_right()
-        sgemm(0, tb, rq, n, rq, rows2, rq, rq * rq, fb_, ldb, sb, img_q, n, rq * n, p, tc=True)
+        sgemm(0, tb, rq, n, rq, rows2, lrq, rq * lrq, fb_, ldb, sb, img_q, ldn, rq * ldn, p, tc=True)
         tb, fb_, ldb, sb = sp.ft_right()
-        sgemm(0, tb, rq, n, rp, pt, rp, rq * rp, fb_, ldb, sb, img_p, n, rq * n, p, tc=True)
+        sgemm(0, tb, rq, n, rp, pt, lrp, rq * lrp, fb_, ldb, sb, img_p, ldn, rq * ldn, p, tc=True)
 
         def side_operator(side, img_other, own, own_ld):
             """Gram side: Y = I_o^T I_o (N x N).  Direct side: T = I_o^T own (N x D)."""
             if side.direct:
                 t = _f32(p, n, side.d, device=dev)
-                sgemm(1, 0, n, side.d, rq, img_other, n, rq * n, own, own_ld, rq * own_ld, t,
+                sgemm(1, 0, n, side.d, rq, img_other, ldn, rq * ldn, own, own_ld, rq * own_ld, t,
                       side.d, n * side.d, p, tc=True)
                 return None, t
-            y = _f32(p, n, n, device=dev)
-            sgemm(1, 0, n, n, rq, img_other, n, rq * n, img_other, n, rq * n, y, n, n * n, p, tc=True)
+            y = _mat(p, n, n, dev)
+            sgemm(1, 0, n, n, rq, img_other, ldn, rq * ldn, img_other, ldn, rq * ldn, y, ldn, n * ldn, p, tc=True)
             return y, None
 
-        y_p, t_p = side_operator(sp, img_q, pt, rp)
-        y_q, t_q = side_operator(sq, img_p, rows2, rq)
+        y_p, t_p = side_operator(sp, img_q, pt, lrp)
+        y_q, t_q = side_operator(sq, img_p, rows2, lrq)
         (m_a, g_a), (m_b, g_b) = ((y_q, t_q), (y_p, t_p)) if swap else ((y_p, t_p), (y_q, t_q))
         gw = _f32(e, b, n, device=dev)
-        call("basd_procrustes_grad_prep", ptr(m_a), ptr(m_b), ptr(img_q), ptr(img_p), n, rq, n, rq * n,
-             n, n * n, p, ptr(pic), ptr(nuc), ptr(side_s.diag), ptr(side_t.diag), ptr(w), ptr(totals),
+        call("basd_procrustes_grad_prep", ptr(m_a), ptr(m_b), ptr(img_q), ptr(img_p), n, rq, ldn, rq * ldn,
+             ldn, n * ldn, p, ptr(pic), ptr(nuc), ptr(side_s.diag), ptr(side_t.diag), ptr(w), ptr(totals),
              ptr(f), ptr(gw), 1, stream())
         if g_a is not None:
             call("basd_procrustes_direct_grad", ptr(side_s.tok), ptr(g_a), ptr(w), n, d_s, p, stream())
         if g_b is not None:
             call("basd_procrustes_direct_grad", ptr(side_t.tok), ptr(g_b), ptr(w), n, d_t, p, stream())
     else:
-        call("basd_procrustes_grad_prep", None, None, None, None, n, rq, n, rq * n, n, n * n, p, None,
+        call("basd_procrustes_grad_prep", None, None, None, None, n, rq, ldn, rq * ldn, ldn, n * ldn, p, None,
              ptr(nuc), ptr(side_s.diag), ptr(side_t.diag), ptr(w), ptr(totals), ptr(f), None, 0, stream())
     geo_terms = _f32(e, device=dev)
     geo = _f32((), device=dev)
@@ -572,19 +612,20 @@ def procrustes_backward(students, teachers, stats: Stats, pro: ProcrustesState,
     b, n_t, d_t = teachers[0].shape
     d_s = students[0].shape[2]
     n = n_student
-    p, nn = e * b, n * n
+    ldn = _pad4(n)
+    p, nn = e * b, n * ldn
     go = grad_out.detach().to(torch.float32).reshape(1).contiguous()
     scale = 1.0 / (e * b)                                # d geo / d f_{i,b}
     if pro.m_a is not None:
         sdt = students[0].dtype
         grad_s = torch.empty(e, b, n, d_s, dtype=sdt, device=dev)
         if all(s.dtype == sdt for s in students) and gemm_tc_ex(
-                0, 0, n, d_s, n, pro.m_a, n, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
+                0, 0, n, d_s, n, pro.m_a, ldn, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
                 alpha=scale, alpha_dev=go):
             outs = [grad_s[i] for i in range(e)]           # written in the token dtype by the epilogue
         else:
             grad_s = _f32(e, b, n, d_s, device=dev)
-            sgemm(0, 0, n, d_s, n, pro.m_a, n, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
+            sgemm(0, 0, n, d_s, n, pro.m_a, ldn, nn, pro.a, d_s, n * d_s, grad_s, d_s, n * d_s, p,
                   alpha=scale, alpha_dev=go, tc=True)
             outs = [_cast_like(grad_s[i], s) for i, s in enumerate(students)]
     else:
@@ -597,7 +638,7 @@ def procrustes_backward(students, teachers, stats: Stats, pro: ProcrustesState,
             outs.append(out)
     z = _f32(e, b, n, d_t, device=dev)
     if pro.m_b is not None:
-        sgemm(0, 0, n, d_t, n, pro.m_b, n, nn, pro.bm, d_t, n * d_t, z, d_t, n * d_t, p,
+        sgemm(0, 0, n, d_t, n, pro.m_b, ldn, nn, pro.bm, d_t, n * d_t, z, d_t, n * d_t, p,
               alpha=scale, alpha_dev=go, tc=True)
     else:
         call("basd_scale_out", ptr(pro.g_b), ptr(z), nat.F32, z.numel(), scale, ptr(go), stream())

@@ -43,8 +43,11 @@ _SIG = {
     "basd_scale_rows_dsigma": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "basd_omega_accumulate": [_p, _p, _p, _i, _i, _i, _p, _p],
     "basd_symmetrize_add": [_p, _i, _p, _i, _p],
+    "basd_projector_complement": [_p, _i, _p, _i, _p],
+    "basd_place_complement": [_p, _p, _p, _i, _i, _p],
     "basd_attn_rows": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "basd_mix_interp": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p],
+    "basd_mix_flat": [_p, _i, _i, _p, _i, _l, _p, _p],
     "basd_mix_rows": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "basd_weight_grad_slices": [],
     "basd_weight_grad": [_p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],
@@ -131,6 +134,7 @@ def stream() -> int:
 # every C-ABI call is bracketed by events recorded on the launching stream.
 _timeline = None
 launch_count = 0
+gemm_flops = {}          # entry point -> fp32-equivalent flops of its launches while the timeline is on
 
 
 def start_timeline():
@@ -150,6 +154,10 @@ def call(name: str, *args):
     global launch_count
     launch_count += 1
     if _timeline is not None:
+        if name.startswith("basd_gemm_tc3_batched"):      # args: ta, tb, m, n, k, ... batch
+            m, n, k = args[2], args[3], args[4]
+            batch = args[14] if name == "basd_gemm_tc3_batched" else args[16]
+            gemm_flops[name] = gemm_flops.get(name, 0.0) + 2.0 * m * n * k * batch
         a = torch.cuda.Event(enable_timing=True)
         b = torch.cuda.Event(enable_timing=True)
         a.record()

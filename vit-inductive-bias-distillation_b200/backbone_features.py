@@ -7,6 +7,7 @@ behind ``forward_features``; random images are run through them and tokens / att
 with ``capture.py`` exactly as the reference's trainer does (src/training/trainer.py:16-37,
 src/models/teacher.py:180-216).
 """
+import math
 import types
 
 import torch
@@ -103,9 +104,31 @@ class ResNetFeatures(nn.Module):
         return self.body(x)
 
 
-def vit(name, seed, classes=1000, img=224, patch=16):
+def fan_in_init(model: nn.Module) -> None:
+    """The reference re-initialises every STUDENT it builds (train.py:19-32, applied at :41-56): linear
+    weights truncated-normal with std sqrt(2 / fan_in) and zero bias, LayerNorm to (1, 0), convolutions
+    normal with std sqrt(2 / fan_out).  Teachers keep their library initialisation."""
+    for m in model.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=math.sqrt(2.0 / m.in_features))
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.Conv2d):
+            fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels // m.groups
+            nn.init.normal_(m.weight, std=math.sqrt(2.0 / fan_out))
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+
+
+def vit(name, seed, classes=1000, img=224, patch=16, student=False):
     torch.manual_seed(seed)
-    return VisionTransformer(*VIT[name], img=img, patch=patch, classes=classes).eval()
+    model = VisionTransformer(*VIT[name], img=img, patch=patch, classes=classes)
+    if student:
+        fan_in_init(model)
+    return model.eval()
 
 
 def vit_teacher(model):
@@ -128,7 +151,7 @@ def backbone_inputs(student_name, teacher_name, layers, batch, *, seed=0, device
     attention).  ``seed`` draws the images and targets, ``model_seed`` the weights (data-parallel
     ranks share the models and differ in their images)."""
     gen = torch.Generator().manual_seed(seed)
-    student = vit(student_name, 100 + model_seed, classes, img, patch).to(device)
+    student = vit(student_name, 100 + model_seed, classes, img, patch, student=True).to(device)
     paths = [f"blocks.{i}" for i in range(len(student.blocks))]
     if teacher_name == "resnet50":
         teacher = cnn_teacher(200 + model_seed)

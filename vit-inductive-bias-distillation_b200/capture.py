@@ -100,10 +100,15 @@ def extract_intermediates(teacher, x: torch.Tensor, *, full_maps: bool = False):
 
 def extract_student(model: torch.nn.Module, x: torch.Tensor, layer_indices: list[int], *,
                     layer_paths: list[str], has_cls_token: bool):
-    """(logits, {layer index: tokens without CLS}) -- reference: trainer.py:16-37."""
+    """(logits, {layer index: tokens without CLS}) -- reference: trainer.py:16-37.  ``model`` may be
+    wrapped (DistributedDataParallel / accelerate): the hooks go on the inner module's blocks, the
+    forward runs through the wrapper so that its gradient hooks fire."""
     hooks, captured = [], {}
+    inner = model
+    while hasattr(inner, "module") and isinstance(getattr(inner, "module"), torch.nn.Module):
+        inner = inner.module
     for idx in layer_indices:
-        block = model.get_submodule(layer_paths[idx])
+        block = inner.get_submodule(layer_paths[idx])
 
         def make_token_hook(i, _has_cls=has_cls_token):
             def hook(mod, inp, out):

@@ -399,6 +399,68 @@ __global__ void weight_grad_finish_kernel(const float* __restrict__ partial, int
   if (threadIdx.x == 0) d_weights[i * L + l] = s;
 }
 
+// Flat layer mix for GrassmannianLayerSelector.forward's reference-shaped outputs (the mixed full
+// attention maps, layer_selector.py:112): out[i][x] = sum_l w[i,l] layer_l[x] over `numel` elements of any
+// shape, all E outputs in ONE pass over the L inputs, 128-bit loads on the aligned body, scalar tail.
+template <typename T, int NE>
+__global__ void __launch_bounds__(256)
+mix_flat_kernel(LayerPtrs layers, int L, int E, const float* __restrict__ weights, long numel,
+                T* __restrict__ out) {
+  __shared__ float w[MAX_E * MAX_L];
+  for (int i = threadIdx.x; i < E * L; i += blockDim.x) w[i] = weights[i];
+  __syncthreads();
+  constexpr int V = 16 / sizeof(T);                      // elements per 128-bit access
+  const long groups = numel / V;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long)gridDim.x * blockDim.x) {
+    float acc[NE][V];
+#pragma unroll
+    for (int i = 0; i < NE; ++i)
+#pragma unroll
+      for (int c = 0; c < V; ++c) acc[i][c] = 0.f;
+    for (int l = 0; l < L; ++l) {
+      float v[V];
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(layers.p[l]) + g * V));
+      if (sizeof(T) == 2) {
+        const uint32_t q[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          v[(2 * c) % V] = __uint_as_float(q[c] << 16);
+          v[(2 * c + 1) % V] = __uint_as_float(q[c] & 0xffff0000u);
+        }
+      } else {
+        v[0] = __uint_as_float(raw.x); v[1 % V] = __uint_as_float(raw.y);
+        v[2 % V] = __uint_as_float(raw.z); v[3 % V] = __uint_as_float(raw.w);
+      }
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        if (i < E) {
+          const float wi = w[i * L + l];
+#pragma unroll
+          for (int c = 0; c < V; ++c) acc[i][c] = fmaf(wi, v[c], acc[i][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      if (i < E) {
+        T* dst = out + (long)i * numel + g * V;
+#pragma unroll
+        for (int c = 0; c < V; ++c) dst[c] = from_f32<T>(acc[i][c]);
+      }
+    }
+  }
+  // tail (numel % V elements) and nothing else: one thread each in the first block
+  const long tail0 = groups * V;
+  if (blockIdx.x == 0 && tail0 + threadIdx.x < numel) {
+    const long x = tail0 + threadIdx.x;
+    for (int i = 0; i < E; ++i) {
+      float a = 0.f;
+      for (int l = 0; l < L; ++l) a = fmaf(w[i * L + l], to_f32<T>(reinterpret_cast<const T*>(layers.p[l])[x]), a);
+      out[(long)i * numel + x] = from_f32<T>(a);
+    }
+  }
+}
+
 }  // namespace basd
 
 using namespace basd;
@@ -458,6 +520,33 @@ extern "C" int basd_mix_interp(const void* const* teacher_layers, int L, int E, 
     return -8;
 #undef BASD_MIX_E
 #undef BASD_MIX
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+// out: (E, numel) in the layers' dtype.  Layer pointers must be 16-byte aligned (torch allocations are;
+// otherwise -9); outputs are written element-wise, so any numel works.
+extern "C" int basd_mix_flat(const void* const* layers, int L, int E, const float* weights, int dtype,
+                             long numel, void* out, void* stream) {
+  if (E > MAX_E || E < 1) return -7;
+  LayerPtrs lp;
+  if (int rc = fill_layers(lp, layers, L)) return rc;
+  const int elt = dtype == BASD_DTYPE_BF16 ? 2 : 4;
+  uintptr_t bits = 0;
+  for (int l = 0; l < L; ++l) bits |= reinterpret_cast<uintptr_t>(layers[l]);
+  if (bits & 15) return -9;
+  const long groups = numel / (16 / elt);
+  const unsigned grid = (unsigned)min((long)148 * 8, max(1L, (groups + 255) / 256));
+#define BASD_FLAT(T)                                                                                 \
+  do {                                                                                               \
+    if (E <= 1) mix_flat_kernel<T, 1><<<grid, 256, 0, ST>>>(lp, L, E, weights, numel, (T*)out);      \
+    else if (E <= 2) mix_flat_kernel<T, 2><<<grid, 256, 0, ST>>>(lp, L, E, weights, numel, (T*)out); \
+    else if (E <= 4) mix_flat_kernel<T, 4><<<grid, 256, 0, ST>>>(lp, L, E, weights, numel, (T*)out); \
+    else mix_flat_kernel<T, 8><<<grid, 256, 0, ST>>>(lp, L, E, weights, numel, (T*)out);             \
+  } while (0)
+  if (dtype == BASD_DTYPE_BF16) BASD_FLAT(__nv_bfloat16);
+  else BASD_FLAT(float);
+#undef BASD_FLAT
   BASD_LAUNCH_CHECK();
   return 0;
 }

@@ -276,6 +276,32 @@ __global__ void symmetrize_add_kernel(const float* __restrict__ in, int D, float
   out[(long)prob * D * D + idx] = m[(long)i * D + j] + m[(long)j * D + i];
 }
 
+// ---- null-space completion (fewer token rows than dimensions, layer_selector.py:14-15 regime) ----
+// sym_eig leaves the eigenvector rows of a rank-deficient Gram beyond its rank r as zeros.  The thin-SVD
+// backward needs them: its (I - V V^T) term acts on exactly that complement.  P = I - V_r^T V_r is the
+// orthogonal projector onto it, and the pivoted Cholesky factor of a projector has orthonormal columns
+// (P = L L^T and P^2 = P give L^T L = I), so rows 0..D-r-1 of LT are an orthonormal basis of the null space.
+__global__ void projector_complement_kernel(const float* __restrict__ vtv, int D, float* __restrict__ P) {
+  const int prob = blockIdx.y;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)D * D) return;
+  const int i = idx / D, j = idx % D;
+  const float* g = vtv + (long)prob * D * D;
+  P[(long)prob * D * D + idx] = (i == j ? 1.f : 0.f) - 0.5f * (g[(long)i * D + j] + g[(long)j * D + i]);
+}
+
+// Vt rows r..D-1 (zeros) <- LT rows 0..D-r-1, r = D - rank_P[problem]
+__global__ void place_complement_kernel(float* __restrict__ Vt, const float* __restrict__ LT,
+                                        const int* __restrict__ rank_p, int D) {
+  const int prob = blockIdx.y;
+  const int nfill = min(rank_p[prob], D);
+  const int r = D - nfill;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)nfill * D) return;
+  const int i = idx / D, c = idx % D;
+  Vt[((long)prob * D + r + i) * D + c] = LT[((long)prob * D + i) * D + c];
+}
+
 }  // namespace basd
 
 using namespace basd;
@@ -361,6 +387,23 @@ extern "C" int basd_omega_accumulate(const float* block, const float* lam_s, con
                                      int E, int L, float* omega, void* stream) {
   dim3 grid(blocks_for((long)D * D, 256), E);
   omega_accumulate_kernel<<<grid, 256, 0, ST>>>(block, lam_s, ranks, D, L, omega);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_projector_complement(const float* vtv, int D, float* P, int batch, void* stream) {
+  if (batch <= 0) return 0;
+  dim3 grid(blocks_for((long)D * D, 256), batch);
+  projector_complement_kernel<<<grid, 256, 0, ST>>>(vtv, D, P);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_place_complement(float* Vt, const float* LT, const int* rank_p, int D, int batch,
+                                     void* stream) {
+  if (batch <= 0) return 0;
+  dim3 grid(blocks_for((long)D * D, 256), batch);
+  place_complement_kernel<<<grid, 256, 0, ST>>>(Vt, LT, rank_p, D);
   BASD_LAUNCH_CHECK();
   return 0;
 }

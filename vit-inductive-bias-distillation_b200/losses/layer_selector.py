@@ -7,6 +7,7 @@ and ``forward`` signature.  The arithmetic runs in libbasd_b200.so (DESIGN.md §
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import types
 
@@ -15,7 +16,7 @@ import torch.nn as nn
 
 from .. import _engine as eng
 from .._autograd import MixingWeights, StepContext, world_size
-from .._native import call, ptr, stream
+from .._native import call, dtype_code, ptr, stream
 
 
 @torch.no_grad()
@@ -149,24 +150,49 @@ class GrassmannianLayerSelector(nn.Module):
             sweeps=dict(sel.sweeps))
         return weights, step
 
+    @torch.no_grad()
+    def mixed_importance(self, weights, step, n_out=None):
+        """The importance-row form of the mixed attention (what relational.py:22-34 reduces the mixed map
+        to): (E, B, n_out) rows, sum_l w[i,l] row_l resampled to n_out tokens and normalised per sample."""
+        rows = step.stats.rows
+        l, b, n_rows = rows.shape
+        w = weights.detach().float().contiguous()
+        e = w.shape[0]
+        n_out = n_rows if n_out is None else n_out
+        out = torch.empty(e, b, n_out, dtype=torch.float32, device=rows.device)
+        totals = torch.empty(e, b, dtype=torch.float32, device=rows.device)
+        call("basd_mix_rows", ptr(rows), ptr(w), e, l, b, n_rows, n_out, ptr(out), ptr(totals), stream())
+        return out
+
     def forward(self, student_tokens_per_layer, all_teacher_tokens, all_teacher_attns,
                 extraction_indices):
         """Reference-shaped entry (:116-152): dicts of mixed teacher tokens (B,N_t,D_t) and
         mixed attention maps keyed by student layer.  The weights come from the kernels;
         materialising the full mixed maps is only done here, for API compatibility --
-        BASDLoss never does it."""
+        BASDLoss never does it (it mixes the (B, N) importance rows: `mixed_importance`)."""
         # the mixing weights do not depend on the attention maps; the flag only tells the statistics
         # stage how to read them: (B,H,N_t+1,N_t+1) maps carry a CLS row, (B,1,N_t,N_t) maps do not
         keys = sorted(all_teacher_tokens.keys())
         a0, n_t = all_teacher_attns[keys[0]], all_teacher_tokens[keys[0]].shape[1]
         has_cls = not (a0.dim() == 4 and a0.shape[-1] == n_t)
-        weights, _ = self.mixing_weights(student_tokens_per_layer, all_teacher_tokens,
-                                         all_teacher_attns, extraction_indices, has_cls=has_cls)
-        tok = torch.stack([all_teacher_tokens[k] for k in keys])
-        att = torch.stack([all_teacher_attns[k] for k in keys])
-        mixed_tok, mixed_att = {}, {}
-        for i, layer in enumerate(extraction_indices):
-            w = weights[i].to(tok.dtype)
-            mixed_tok[layer] = (w.view(-1, 1, 1, 1) * tok).sum(dim=0)
-            mixed_att[layer] = (w.to(att.dtype).view(-1, 1, 1, 1, 1) * att).sum(dim=0)
+        weights, step = self.mixing_weights(student_tokens_per_layer, all_teacher_tokens,
+                                            all_teacher_attns, extraction_indices, has_cls=has_cls)
+        # one pass over the teacher stack / the attention stack for all E outputs (mix.cu); gradients
+        # flow through `weights` only inside BASDLoss (ProcrustesGeo), these dicts are detached
+        w = weights.detach().float().contiguous()
+        e, l = w.shape
+        toks = step.teachers
+        b, n_t, d_t = toks[0].shape
+        mixed = torch.empty(e, b, n_t, d_t, dtype=toks[0].dtype, device=w.device)
+        tptrs = (ctypes.c_void_p * l)(*[t.data_ptr() for t in toks])
+        call("basd_mix_interp", tptrs, l, e, ptr(w), dtype_code(toks[0]), b, n_t, n_t, d_t, ptr(mixed),
+             dtype_code(mixed), stream())
+        atts = [all_teacher_attns[k].contiguous() for k in keys]
+        if any(a.shape != atts[0].shape or a.dtype != atts[0].dtype for a in atts):
+            raise ValueError("teacher attention maps must share one shape and dtype")
+        mixed_a = torch.empty((e,) + tuple(atts[0].shape), dtype=atts[0].dtype, device=w.device)
+        aptrs = (ctypes.c_void_p * l)(*[a.data_ptr() for a in atts])
+        call("basd_mix_flat", aptrs, l, e, ptr(w), dtype_code(atts[0]), atts[0].numel(), ptr(mixed_a), stream())
+        mixed_tok = {layer: mixed[i] for i, layer in enumerate(extraction_indices)}
+        mixed_att = {layer: mixed_a[i] for i, layer in enumerate(extraction_indices)}
         return mixed_tok, mixed_att
