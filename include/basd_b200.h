@@ -40,18 +40,28 @@ int basd_sgemm_batched(int trans_a, int trans_b, int M, int N, int K, const void
                        long stride_b, float* C, int ldc, long stride_c, int batch, float alpha,
                        const float* alpha_dev, float beta, void* stream);
 
+/* ---- mean-shifted token statistics ----------------------------------------------------- */
+
+/* The pooled covariance behind the MP rank and the layer subspaces (layer_selector.py:13,35,72,88,91) is
+ * accumulated in a frame shifted by a rough mean mu0 (covariance is shift invariant), so that the Gram
+ * accumulators never hold the M mu mu^T term the centring would have to cancel afterwards (DESIGN.md
+ * section 3.1).  mu0[i] = mean of the first rows_sample rows of tensor i (count tensors, one launch).  The
+ * Gram entry points below take mu0 (bf16-representable values) and return the statistics of x - mu0. */
+int basd_rough_means(const void* const* tensors, int count, int dtype, long rows, int D, long rows_sample,
+                     float* mu0, void* stream);
+
 /* Token-space second-moment statistics of one (rows x D) token matrix:
  * gram = X^T X (D x D, symmetric), colsum = X^T 1 (D).  Deterministic split-K.
  * Replaces `features.T @ features` (layer_selector.py:13) and the column mean (:35,:91);
  * the fixed projections proj_s/proj_t are applied to the small matrix afterwards. */
 long basd_token_gram_simt_workspace_floats(long rows, int D);
-int basd_token_gram_simt(const void* tokens, int dtype, long rows, int D, float* gram,
+int basd_token_gram_simt(const void* tokens, int dtype, long rows, int D, const float* mu0, float* gram,
                          float* colsum, float* workspace, void* stream);
 
 /* Same statistic on the tensor cores (gram_tc.cu): TMA-fed tcgen05.mma (bf16 x bf16 -> fp32 in
  * TMEM), 128x128 upper-triangular tiles, split-K over the token rows. bf16 tokens, D % 128 == 0. */
 long basd_token_gram_tc_workspace_bytes(long rows, int D);
-int basd_token_gram_tc(const void* tokens, long rows, int D, float* gram, float* colsum,
+int basd_token_gram_tc(const void* tokens, long rows, int D, const float* mu0, float* gram, float* colsum,
                        void* workspace, void* stream);
 
 /* ---- small-matrix factorisations (jacobi.cu) ---------------------------------------- */
@@ -70,6 +80,17 @@ int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, float* LT, int
  * Requires ld % 4 == 0, stride % 4 == 0, 16-byte aligned base, m <= 1024. */
 int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
                      float tol, int max_sweeps, int* sweeps_out, void* stream);
+
+/* General form.  dims (square active size) and row_dims (leading non-zero rows) are mutually exclusive,
+ * either may be null.  Two thresholds on the cosine between rows: a pair is rotated while |cos| > tol; the
+ * sweeps stop after one in which every rotated pair had |cos| < stop_cos.  The entry points above and below
+ * use stop_cos = sqrt(tol) (quadratic convergence of the sweep): enough for singular values and polar
+ * factors.  Eigenvectors of a dense spectrum need stop_cos << relative eigenvalue gap (rows with nearly
+ * equal norms keep mixing by cos / gap): the selector's symmetric eigenproblems pass 1e-5.
+ * (torch.linalg.svd at layer_selector.py:36,92) */
+int basd_jacobi_rows_ex(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                        const int* row_dims, float tol, float stop_cos, int max_sweeps, int* sweeps_out,
+                        int* rot_out, void* stream);
 
 /* Rank-deficient products G = F_q^T F_p: only the first row_dims[problem] rows are non-zero (the
  * pivoted-Cholesky rank); sweeps over those rows only.  row_dims may be null (= basd_jacobi_rows). */
@@ -141,11 +162,18 @@ int basd_omega_accumulate(const float* block, const float* lam_s, const int* ran
                           int L, float* omega, void* stream);
 int basd_symmetrize_add(const float* in, int D, float* out, int batch, void* stream);
 
-/* Null-space completion for rank-deficient student Grams (fewer token rows than dimensions, the regime of
- * layer_selector.py:14-15): P = I - sym(vtv) with vtv = V_r^T V_r; after basd_pivoted_cholesky(P) rows
- * 0..rank_P-1 of its factor are an orthonormal basis of the complement and are written into the zero rows
- * D-rank_P..D-1 of Vt -- what the (I - V V^T) term of the thin-SVD backward (layer_selector.py:92) needs. */
-int basd_projector_complement(const float* vtv, int D, float* P, int batch, void* stream);
+/* K <- K + rel_shift * max(diag K) * I per problem: same eigenvectors, and the pivoted Cholesky behind the
+ * symmetric eigenproblems (torch.linalg.svd / eigvalsh at layer_selector.py:16,36,92) never meets a
+ * noise-sized pivot on a nearly singular Gram. */
+int basd_shift_diag(float* K, int D, float rel_shift, int batch, void* stream);
+
+/* Null-space completion for numerically rank-deficient student Grams (fewer token rows than dimensions, the
+ * regime of layer_selector.py:14-15, or eigenvalues below the fp32 floor): P = I - sym(vtv) with
+ * vtv = V_r^T V_r, dims_out[problem] = D if rows are missing else 0 (the `dims` of the Cholesky that follows,
+ * so complete bases cost nothing); after basd_pivoted_cholesky(P) rows 0..rank_P-1 of its factor are an
+ * orthonormal basis of the complement and are written into the zero rows D-rank_P..D-1 of Vt -- what the
+ * (I - V V^T) term of the thin-SVD backward (layer_selector.py:92) needs. */
+int basd_projector_complement(const float* vtv, int D, float* P, int* dims_out, int batch, void* stream);
 int basd_place_complement(float* Vt, const float* LT, const int* rank_p, int D, int batch, void* stream);
 
 /* ---- HBM-bound mixing (mix.cu) ------------------------------------------------------ */

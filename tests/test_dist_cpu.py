@@ -42,12 +42,32 @@ def _worker(rank, world, port, local_batch, out):
         work = cs.workload("c1", local_batch)
         _, _, st, te, _ = syn.make_inputs(work, seed=4, batch_offset=rank * local_batch)
         layers = sorted(st)
-        flat, sizes = _pack([km.token_stats(st[l]) for l in layers],
-                            [km.token_stats(te[k]) for k in sorted(te)])
+        # the ranks first agree on the shift (mean of their rough means), then shift, then add statistics:
+        # the contract of _engine.statistics (center.cu)
+        tensors = [st[l] for l in layers] + [te[k] for k in sorted(te)]
+        mu0 = torch.cat([t.reshape(-1, t.shape[-1])[:256].mean(0) for t in tensors])
+        _engine._all_reduce(mu0, None)
+        mu0 = mu0 / world
+        shifts, o = [], 0
+        for t in tensors:
+            shifts.append(mu0[o:o + t.shape[-1]])
+            o += t.shape[-1]
+        shifted = [t - m for t, m in zip(tensors, shifts)]
+        flat, sizes = _pack([km.token_stats(x) for x in shifted[:len(layers)]],
+                            [km.token_stats(x) for x in shifted[len(layers):]])
         _engine._all_reduce(flat, None)                       # the product's collective helper
         stats_s, stats_t = _unpack(flat, sizes, len(layers), len(te), work.d_student, work.d_teacher)
-        proj_s, proj_t, logt = cs.selector_state(work)
         rows = world * local_batch * work.n_student
+
+        def unshift(stat, m):                                 # back to the unshifted frame the CPU model takes
+            g, c = stat[0].double(), stat[1].double()
+            m = m.double()
+            return ((g + torch.outer(m, c) + torch.outer(c, m) + rows * torch.outer(m, m)).float(),
+                    (c + rows * m).float())
+
+        stats_s = [unshift(x, m) for x, m in zip(stats_s, shifts[:len(layers)])]
+        stats_t = [unshift(x, m) for x, m in zip(stats_t, shifts[len(layers):])]
+        proj_s, proj_t, logt = cs.selector_state(work)
         sel = km.selector_model(stats_s, stats_t, rows, rows, proj_s, proj_t, logt)
         if rank == 0:
             out.put((sel["ranks"], torch.stack(sel["weights"]).tolist()))

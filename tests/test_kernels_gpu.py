@@ -118,6 +118,31 @@ def test_token_gram(dtype, rows, d):
     assert (gram - gram.T).abs().max() == 0
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,d", [(4 * 196, 384), (3001, 200), (50176, 384), (6272, 768), (50, 128)])
+def test_token_gram_in_a_mean_shifted_frame(dtype, rows, d):
+    """Large token means (|mu|^2 = 100 x the variance): the Gram and column sums of x - mu0 must come out with
+    the accuracy of the COVARIANCE scale, not of M |mu|^2 -- the shift is worked into the accumulation
+    (one negated UMMA per 64-row stage on the tensor-core path), the tokens are not rounded."""
+    eng = _eng()
+    torch.manual_seed(5)
+    mu = 10.0 * torch.randn(d, device=DEV)
+    x = (torch.randn(rows, d, device=DEV) * torch.logspace(0, -1, d, device=DEV) + mu).to(dtype)
+    mu0 = x[:min(rows, 4096)].float().mean(0).to(torch.bfloat16).float()
+    gram = torch.empty(d, d, device=DEV)
+    col = torch.empty(d, device=DEV)
+    eng.token_gram(x.view(1, rows, d), gram, col, mu0)
+    xs = x.double() - mu0.double()
+    ref = xs.T @ xs
+    scale = float(ref.diagonal().max())                  # covariance scale (the shifted frame's largest entry)
+    err = float((gram.double() - ref).abs().max())
+    raw_scale = float((x.double().T @ x.double()).abs().max())
+    print(f"rows {rows} d {d} {dtype}: max err / cov scale {err / scale:.2e} (uncentred scale is {raw_scale / scale:.0f}x)")
+    assert err / scale < 2e-5
+    assert (col.double() - xs.sum(0)).abs().max() < 1e-4 * max(1.0, float(xs.sum(0).abs().max()))
+    assert (gram - gram.T).abs().max() == 0
+
+
 @pytest.mark.parametrize("n,rank", [(64, 64), (196, 195), (196, 48), (384, 384)])
 def test_pivoted_cholesky(n, rank):
     eng = _eng()

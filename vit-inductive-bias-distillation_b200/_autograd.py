@@ -127,7 +127,7 @@ class MixingWeights(torch.autograd.Function):
         step.teachers = [t.detach().contiguous() for t in step.teachers]
         _check_inputs(students, step)
         logt = log_temps.detach().to(torch.float32).contiguous()
-        stats, flat = eng.statistics(students, step.teachers, step.attns, step.has_cls)
+        stats, flat = eng.statistics(students, step.teachers, step.attns, step.has_cls, step.group, step.world)
         if step.world > 1:
             eng._all_reduce(flat, step.group)
         b, n_s, _ = students[0].shape

@@ -24,10 +24,22 @@ import os as _os
 # measured them: tests/tools/floor_sweep.py, tests/tools/parity_report.py).
 JACOBI_TOL = 1e-6        # |cos| between two rows below which they count as orthogonal
 JACOBI_SWEEPS = 18       # sweep cap (C2 backbone features converge in 8-11)
+# Symmetric eigenproblems of the selector Grams: the sweeps end only when every rotated pair had |cos| below
+# this.  The default sqrt(tol) = 1e-3 leaves rows of nearly equal norm mixed by ~cos / (relative gap); with
+# 50,176 token rows the spectrum is dense (gaps ~1e-3 at the MP rank boundary) and the selector gradient came
+# out with cosine 0.87 against autograd through the reference (C2, B = 256) while every small-batch case passed.
+EIG_STOP_COS = 1e-3
 PROC_JACOBI_TOL = 1e-6   # per-sample Procrustes SVDs: loosening costs gradient parity before it saves a sweep
 CHOL_TOL = 1e-5          # pivoted-Cholesky rank cut (per-sample N x N Grams), relative to the
                          # largest diagonal: just above the fp32 accumulation noise of K
-GRAM_CHOL_TOL = 1e-7     # same for the D x D selector Grams
+GRAM_CHOL_TOL = 1e-7     # same for the D x D selector Grams (after the diagonal shift below it never triggers)
+# sym_eig factors K + GRAM_SHIFT * max(diag K) * I: identical eigenvectors, and no noise-sized pivots when
+# fp32 rounding has pushed the smallest eigenvalues of a nearly singular Gram to zero or below.  Measured
+# without it (C2, B = 256): one eigenvalue at -5e-5 lambda_max made the factorisation lose 12 rows and rotated
+# the top-k student subspace by sin 0.6; stopping the factorisation at a higher tolerance instead drops up
+# to (D - r) pivots of mass, more than the eigenvalue gap at the rank boundary (C4: selector gradient 0.88).
+# The eigenvalues themselves come from Rayleigh quotients against the unshifted matrix.
+GRAM_SHIFT = 1e-5        # ~10x the fp32 noise of the Schur complement (sqrt(D) eps max diag)
 SV_FLOOR = 1e-6          # k x k principal-angle SVD: directions below this are dropped
 ROW_FLOOR = 1e-7         # rows this far below the largest row norm are numerically zero in fp32
 # Procrustes with a Gram side: singular directions of G = F_q^T F_p below this fraction of sigma_max
@@ -112,20 +124,22 @@ def gemm_tc_ex(ta, tb, m, n, k, a, lda, sa, b, ldb, sb, c, ldc, sc, batch=1, alp
     return True
 
 
-def token_gram(tokens: torch.Tensor, gram: torch.Tensor, colsum: torch.Tensor):
-    """gram (D,D) = X^T X, colsum (D) = X^T 1 for X = tokens.reshape(-1, D)."""
+def token_gram(tokens: torch.Tensor, gram: torch.Tensor, colsum: torch.Tensor | None, mu0=None):
+    """gram (D,D) = X'^T X', colsum (D) = X'^T 1 (skipped when None) for X' = tokens.reshape(-1, D) - mu0
+    (mu0: (D,) fp32 with bf16-representable values, or None for no shift).  The tokens themselves are
+    never modified: the kernels work the shift into the accumulation (gram_tc.cu / gemm_simt.cu)."""
     d = tokens.shape[-1]
     rows = tokens.numel() // d
     x = tokens if tokens.is_contiguous() else tokens.contiguous()
     if (x.dtype == torch.bfloat16 and nat.has("basd_token_gram_tc") and d % 128 == 0
-            and x.data_ptr() % 16 == 0):
+            and x.data_ptr() % 16 == 0 and (mu0 is None or colsum is not None)):
         nbytes = nat.load().basd_token_gram_tc_workspace_bytes(rows, d)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        call("basd_token_gram_tc", ptr(x), rows, d, ptr(gram), ptr(colsum), ptr(ws), stream())
+        call("basd_token_gram_tc", ptr(x), rows, d, ptr(mu0), ptr(gram), ptr(colsum), ptr(ws), stream())
         return
     nfl = nat.load().basd_token_gram_simt_workspace_floats(rows, d)
     ws = _f32(nfl, device=x.device)
-    call("basd_token_gram_simt", ptr(x), nat.dtype_code(x), rows, d, ptr(gram), ptr(colsum),
+    call("basd_token_gram_simt", ptr(x), nat.dtype_code(x), rows, d, ptr(mu0), ptr(gram), ptr(colsum),
          ptr(ws), stream())
 
 
@@ -142,31 +156,23 @@ def pivoted_cholesky(k, lt, rel_tol, dims=None, rank_out=None):
 jacobi_log = None
 
 
-def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi", tol=None, row_dims=None, cols=None):
+def jacobi_rows(g, dims=None, sweeps_out=None, tag="jacobi", tol=None, row_dims=None, cols=None, stop_cos=None):
     """dims: active leading size of square problems (rows and columns); row_dims: number of
     leading non-zero rows (rank of the factor the rows come from), all columns active.
-    cols: logical row length when the rows are padded (g.shape[2] is the pitch)."""
+    cols: logical row length when the rows are padded (g.shape[2] is the pitch).
+    stop_cos: the sweeps end after one whose rotated pairs all had |cos| below it (default sqrt(tol):
+    quadratic convergence; eigenvector problems pass EIG_STOP_COS)."""
     batch, n, ld = g.shape
     m = ld if cols is None else cols
     tol = JACOBI_TOL if tol is None else tol
-    if row_dims is not None and dims is None:
-        rot = None
-        if jacobi_log is not None:
-            sweeps_out = sweeps_out if sweeps_out is not None else torch.zeros(batch, dtype=torch.int32, device=g.device)
-            rot = torch.zeros(batch, dtype=torch.int32, device=g.device)
-            jacobi_log.append((tag, n, m, None, sweeps_out, rot, row_dims))
-        call("basd_jacobi_rows_ranked", ptr(g), n, m, ld, n * ld, batch, ptr(row_dims), tol, JACOBI_SWEEPS,
-             ptr(sweeps_out), ptr(rot), stream())
-        return
+    stop_cos = tol ** 0.5 if stop_cos is None else stop_cos
+    rot = None
     if jacobi_log is not None:
         sweeps_out = sweeps_out if sweeps_out is not None else torch.zeros(batch, dtype=torch.int32, device=g.device)
         rot = torch.zeros(batch, dtype=torch.int32, device=g.device)
-        call("basd_jacobi_rows_counted", ptr(g), n, m, ld, n * ld, batch, ptr(dims), tol,
-             JACOBI_SWEEPS, ptr(sweeps_out), ptr(rot), stream())
-        jacobi_log.append((tag, n, m, dims, sweeps_out, rot, None))
-        return
-    call("basd_jacobi_rows", ptr(g), n, m, ld, n * ld, batch, ptr(dims), tol, JACOBI_SWEEPS,
-         ptr(sweeps_out), stream())
+        jacobi_log.append((tag, n, m, dims, sweeps_out, rot, row_dims))
+    call("basd_jacobi_rows_ex", ptr(g), n, m, ld, n * ld, batch, ptr(dims), ptr(row_dims), tol, stop_cos,
+         JACOBI_SWEEPS, ptr(sweeps_out), ptr(rot), stream())
 
 
 def rows_normalize(g, out, vals, *, sort, square, rel_floor, dims=None, cols=None):
@@ -177,19 +183,27 @@ def rows_normalize(g, out, vals, *, sort, square, rel_floor, dims=None, cols=Non
          int(sort), int(square), rel_floor, ptr(dims), stream())
 
 
+last_eig_sweeps = []      # per sym_eig call of the current step (diagnostics: SelectorState.sweeps["eig"])
+
+
 def sym_eig(kmats: torch.Tensor):
     """Batched symmetric PSD eigendecomposition: returns (lam (b,D) descending, Vt (b,D,D)
-    with eigenvectors as rows). Pivoted Cholesky -> row-Jacobi on the factor -> sort ->
-    Rayleigh-quotient refinement against the untouched matrix."""
+    with eigenvectors as rows). Pivoted Cholesky -> row-Jacobi on the factor -> sort -> completion of
+    the directions behind the rank cut -> Rayleigh-quotient refinement against the untouched matrix
+    (the completed rows are a basis of the numerical null space, their lam are its Rayleigh quotients)."""
     batch, d, _ = kmats.shape
     dev = kmats.device
     work = kmats.clone()
+    call("basd_shift_diag", ptr(work), d, GRAM_SHIFT, batch, stream())
     lt = _f32(batch, d, d, device=dev)
     pivoted_cholesky(work, lt, GRAM_CHOL_TOL)
-    jacobi_rows(lt, tag="eig")
+    sweeps = torch.zeros(batch, dtype=torch.int32, device=dev)
+    jacobi_rows(lt, tag="eig", stop_cos=EIG_STOP_COS, sweeps_out=sweeps)
+    last_eig_sweeps.append(sweeps)
     vt = work                         # reuse: the Schur complement is dead
     coarse = _f32(batch, d, device=dev)
     rows_normalize(lt, vt, coarse, sort=True, square=True, rel_floor=ROW_FLOOR)
+    complete_null_space(vt)           # rows behind the rank cut: an orthonormal basis of the complement
     kv = lt                           # reuse
     sgemm(0, 0, d, d, d, vt, d, d * d, kmats, d, d * d, kv, d, d * d, batch)
     lam = _f32(batch, d, device=dev)
@@ -198,17 +212,21 @@ def sym_eig(kmats: torch.Tensor):
 
 
 def complete_null_space(vt: torch.Tensor):
-    """In place: the zero rows sym_eig leaves beyond the rank of a deficient Gram become an orthonormal
-    basis of its null space (selector.cu: projector + pivoted Cholesky).  Needed only when there are
-    fewer token rows than dimensions; the thin-SVD backward's (I - V V^T) term lives there."""
+    """In place: the zero rows sym_eig leaves beyond the numerical rank of a Gram become an orthonormal
+    basis of its null space (selector.cu: projector + pivoted Cholesky).  The thin-SVD backward's
+    (I - V V^T) term lives there: with fewer token rows than dimensions (layer_selector.py:14-15), and
+    when a spectrum spanning more than 1/eps pushes an eigenvalue under the row floor (its eigenvector is
+    then the complement of all the others).  Problems whose basis is complete exit at once (device-side
+    `dims`), so the common case costs four small launches."""
     batch, d, _ = vt.shape
     dev = vt.device
     vtv = _f32(batch, d, d, device=dev)
-    sgemm(1, 0, d, d, d, vt, d, d * d, vt, d, d * d, vtv, d, d * d, batch)
+    sgemm(1, 0, d, d, d, vt, d, d * d, vt, d, d * d, vtv, d, d * d, batch, tc=True)
     proj = _f32(batch, d, d, device=dev)
-    call("basd_projector_complement", ptr(vtv), d, ptr(proj), batch, stream())
+    active = torch.empty(batch, dtype=torch.int32, device=dev)
+    call("basd_projector_complement", ptr(vtv), d, ptr(proj), ptr(active), batch, stream())
     rank_p = torch.empty(batch, dtype=torch.int32, device=dev)
-    pivoted_cholesky(proj, vtv, 1e-3, rank_out=rank_p)      # projector eigenvalues are 0 or 1
+    pivoted_cholesky(proj, vtv, 1e-3, dims=active, rank_out=rank_p)      # projector eigenvalues are 0 or 1
     call("basd_place_complement", ptr(vt), ptr(vtv), ptr(rank_p), d, batch, stream())
 
 
@@ -247,10 +265,12 @@ def sharded_sym_eig(kmats: torch.Tensor, group, world: int, solver=None):
 @dataclass
 class Stats:
     gram_s: torch.Tensor      # (E, Ds, Ds) token-space
-    col_s: torch.Tensor       # (E, Ds)
+    col_s: torch.Tensor       # (E, Ds)  column sums in the same (mean-shifted) frame as the Grams
     gram_t: torch.Tensor      # (L, Dt, Dt)
     col_t: torch.Tensor       # (L, Dt)
     rows: torch.Tensor        # (L, B, Nt) attention importance rows (local shard)
+    mu0_s: torch.Tensor | None = None     # (E, Ds) shift applied to the student tokens before the Gram
+    mu0_t: torch.Tensor | None = None     # (L, Dt)
 
 
 def _all_reduce(flat: torch.Tensor, group):
@@ -296,11 +316,23 @@ def importance_rows(attns, b: int, has_cls: bool, dev) -> torch.Tensor:
     return rows
 
 
-def statistics(students, teachers, attns, has_cls):
+ROUGH_MEAN_ROWS = 4096        # token rows behind the rough mean the statistics are shifted by
+
+
+def _ptr_array(tensors):
+    return (nat.C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def statistics(students, teachers, attns, has_cls, group=None, world: int = 1):
+    """Token-space Grams and column sums of every student / teacher tensor, in a MEAN-SHIFTED frame
+    (the Gram kernels subtract a rough mean inside the accumulation so that the accumulators never
+    hold the M mu mu^T term the centring would otherwise have to cancel), plus the importance rows.
+    Returns (Stats, flat) where `flat` is the one buffer data-parallel ranks all-reduce; the ranks agree on
+    the shift first (an all-reduce of E D_s + L D_t floats) so that their statistics add."""
     dev = students[0].device
     e, l = len(students), len(teachers)
     b, n_t, d_t = teachers[0].shape
-    d_s = students[0].shape[2]
+    n_s, d_s = students[0].shape[1], students[0].shape[2]
     # one flat buffer so the data-parallel exchange is a single all-reduce
     sizes = [e * d_s * d_s, e * d_s, l * d_t * d_t, l * d_t]
     flat = _f32(sum(sizes), device=dev)
@@ -311,12 +343,23 @@ def statistics(students, teachers, attns, has_cls):
     col_s = flat[offs[1]:offs[2]].view(e, d_s)
     gram_t = flat[offs[2]:offs[3]].view(l, d_t, d_t)
     col_t = flat[offs[3]:offs[4]].view(l, d_t)
+    mu0 = _f32(e * d_s + l * d_t, device=dev)
+    mu0_s, mu0_t = mu0[:e * d_s].view(e, d_s), mu0[e * d_s:].view(l, d_t)
+    for tensors, nrows, d, m0 in ((students, b * n_s, d_s, mu0_s), (teachers, b * n_t, d_t, mu0_t)):
+        call("basd_rough_means", _ptr_array(tensors), len(tensors), nat.dtype_code(tensors[0]), nrows, d,
+             min(nrows, ROUGH_MEAN_ROWS), ptr(m0), stream())
+    if world > 1:                                         # the ranks' statistics only add under ONE shift
+        _all_reduce(mu0, group)
+        mu0 /= world
+    # the correction operand of the tensor-core Gram holds 8 mu0 in bf16: it must be exact
+    mu0 = mu0.to(torch.bfloat16).to(torch.float32)
+    mu0_s, mu0_t = mu0[:e * d_s].view(e, d_s), mu0[e * d_s:].view(l, d_t)
     for i, s in enumerate(students):
-        token_gram(s, gram_s[i], col_s[i])
+        token_gram(s, gram_s[i], col_s[i], mu0_s[i])
     for j, t in enumerate(teachers):
-        token_gram(t, gram_t[j], col_t[j])
+        token_gram(t, gram_t[j], col_t[j], mu0_t[j])
     rows = importance_rows(attns, b, has_cls, dev)
-    return Stats(gram_s, col_s, gram_t, col_t, rows), flat
+    return Stats(gram_s, col_s, gram_t, col_t, rows, mu0_s, mu0_t), flat
 
 
 def attention_only_stats(teachers, attns, has_cls):
@@ -377,14 +420,21 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
         sgemm(0, 1, e, d_s, d_s, stats.col_s, d_s, 0, proj_s, d_s, 0, chat_s, d_s, 0, 1)
         call("basd_center_gram", ptr(ghat_t), ptr(chat_t), d_s, 1.0 / rows_t, ptr(kall[:l]), l, stream())
         call("basd_center_gram", ptr(ghat_s), ptr(chat_s), d_s, 1.0 / rows_s, ptr(kall[l:]), e, stream())
+    # the statistics live in a mean-shifted frame (statistics()): K is shift invariant, the projected column
+    # SUMS get the shift back (chat = P c' + M P mu0) -- the uncentred spectrum behind the MP rank needs them
+    if stats.mu0_t is not None:
+        sgemm(0, 1, l, d_s, d_t, stats.mu0_t, d_t, 0, proj_t, d_t, 0, chat_t, d_s, 0, 1, alpha=float(rows_t),
+              beta=1.0)
+        sgemm(0, 1, e, d_s, d_s, stats.mu0_s, d_s, 0, proj_s, d_s, 0, chat_s, d_s, 0, 1, alpha=float(rows_s),
+              beta=1.0)
     # --- [centred teacher | centred student] eigenproblems in one batch.  The uncentred teacher
     # spectrum (only needed for the MP rank) follows from the centred one by the rank-one
     # secular equation, so it costs no eigenproblem of its own.
+    last_eig_sweeps.clear()
     lam, vt = sharded_sym_eig(kall, group, world)
+    eig_sweeps = torch.cat(last_eig_sweeps) if last_eig_sweeps else None
     lam_t, lam_s = lam[:l], lam[l:]
     vt_t, vt_s = vt[:l], vt[l:]
-    if rows_s < d_s:          # rank-deficient student Grams: complete the eigenvector basis
-        complete_null_space(vt_s)
     y_t = _f32(l, d_s, device=dev)                        # y = V^T c_hat per teacher layer
     sgemm(0, 0, d_s, 1, d_s, vt_t, d_s, d_s * d_s, chat_t, 1, d_s, y_t, 1, d_s, l)
     ranks = torch.empty(l, dtype=torch.int32, device=dev)
@@ -417,8 +467,10 @@ def selector_forward(stats: Stats, rows_s: int, rows_t: int, proj_s, proj_t, log
     temps = _f32(e, device=dev)
     call("basd_mix_weights", ptr(dist_el), ptr(log_temps), e, l, ptr(weights), ptr(temps), stream())
     mean_s = stats.col_s / float(rows_s)
+    if stats.mu0_s is not None:
+        mean_s = mean_s + stats.mu0_s
     return SelectorState(ranks, edges, lam_t, lam_s, vt_s, wfull, uxt, vxt, sig, dist_el,
-                         weights, temps, mean_s, {"kxk": sweeps})
+                         weights, temps, mean_s, {"kxk": sweeps, "eig": eig_sweeps})
 
 
 @dataclass

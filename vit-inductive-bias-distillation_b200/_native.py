@@ -22,11 +22,13 @@ _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_long, C.c_float
 # name -> argument ctypes (return type is int unless listed in _RET)
 _SIG = {
     "basd_sgemm_batched": [_i, _i, _i, _i, _i, _p, _i, _i, _l, _p, _p, _i, _l, _p, _i, _l, _i, _f, _p, _f, _p],
+    "basd_rough_means": [_p, _i, _i, _l, _i, _l, _p, _p],
     "basd_token_gram_simt_workspace_floats": [_l, _i],
-    "basd_token_gram_simt": [_p, _i, _l, _i, _p, _p, _p, _p],
+    "basd_token_gram_simt": [_p, _i, _l, _i, _p, _p, _p, _p, _p],
     "basd_pivoted_cholesky": [_p, _i, _i, _l, _p, _i, _l, _i, _f, _p, _p, _p],
     "basd_jacobi_rows": [_p, _i, _i, _i, _l, _i, _p, _f, _i, _p, _p],
     "basd_jacobi_rows_counted": [_p, _i, _i, _i, _l, _i, _p, _f, _i, _p, _p, _p],
+    "basd_jacobi_rows_ex": [_p, _i, _i, _i, _l, _i, _p, _p, _f, _f, _i, _p, _p, _p],
     "basd_jacobi_rows_ranked": [_p, _i, _i, _i, _l, _i, _p, _f, _i, _p, _p, _p],
     "basd_rows_normalize": [_p, _i, _i, _i, _l, _p, _i, _l, _p, _i, _i, _i, _f, _p, _p],
     "basd_rowdot": [_p, _i, _l, _p, _i, _l, _i, _i, _i, _p, _p],
@@ -43,7 +45,8 @@ _SIG = {
     "basd_scale_rows_dsigma": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "basd_omega_accumulate": [_p, _p, _p, _i, _i, _i, _p, _p],
     "basd_symmetrize_add": [_p, _i, _p, _i, _p],
-    "basd_projector_complement": [_p, _i, _p, _i, _p],
+    "basd_shift_diag": [_p, _i, _f, _i, _p],
+    "basd_projector_complement": [_p, _i, _p, _p, _i, _p],
     "basd_place_complement": [_p, _p, _p, _i, _i, _p],
     "basd_attn_rows": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "basd_mix_interp": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p],
@@ -65,11 +68,12 @@ _SIG = {
                                  _p, _p],
     "basd_cast_out": [_p, _p, _i, _l, _p],
 }
-_RET = {"basd_token_gram_simt_workspace_floats": _l, "basd_rotate_stats_f64_workspace_bytes": _l}
+_RET = {"basd_token_gram_simt_workspace_floats": _l, "basd_rotate_stats_f64_workspace_bytes": _l,
+        }
 # optional symbols (present once the tcgen05 Gram is built)
 _OPTIONAL = {
     "basd_token_gram_tc_workspace_bytes": ([_l, _i], _l),
-    "basd_token_gram_tc": ([_p, _l, _i, _p, _p, _p, _p], _i),
+    "basd_token_gram_tc": ([_p, _l, _i, _p, _p, _p, _p, _p], _i),
 }
 
 _lib = None

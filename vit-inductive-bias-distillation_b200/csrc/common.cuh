@@ -81,18 +81,19 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float out[8]) {
 
 // gemm_simt.cu helpers reused by gram_tc.cu
 int launch_gram_reduce(const float* partial, int slices, int D, int tile, float* gram,
-                       cudaStream_t st);
+                       cudaStream_t st, const float* mu0 = nullptr, const float* dsum = nullptr,
+                       float coef = 0.f);
 int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial /* >= 64*D floats */,
-                       float* out, cudaStream_t st);
+                       float* out, cudaStream_t st, const float* mu0 = nullptr);
 
 // jacobi_oe8.cu: register-resident Jacobi with eight rows per 16-lane group (<= 224 x 224 active);
 // returns -100 when the shape does not fit.
 int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
-                      float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                      float tol, float stop2, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                       int dim_hi, int* rot_out, int rows_only = 0);
 
 int launch_jacobi_oe8_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
-                              float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                              float tol, float stop2, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                               int dim_hi, int* rot_out);
 
 }  // namespace basd

@@ -287,7 +287,7 @@ sgemm8_kernel(int M, int N, int K, const AT* __restrict__ A, int lda, long sA,
 template <typename T>
 __global__ void __launch_bounds__(256)
 token_gram_partial_kernel(const T* __restrict__ X, long rows, int D, long rows_per_slice,
-                          float* __restrict__ partial) {
+                          float* __restrict__ partial, const float* __restrict__ mu0) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tiles = (D + BM - 1) / BM;
@@ -305,13 +305,19 @@ token_gram_partial_kernel(const T* __restrict__ X, long rows, int D, long rows_p
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const int kk = tid >> 4, dd = (tid & 15) * 4;
+  float ma[4], mb[4];                                    // the shift of this thread's staging columns
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ma[i] = (mu0 && (a0 + dd + i) < D) ? mu0[a0 + dd + i] : 0.f;
+    mb[i] = (mu0 && (b0 + dd + i) < D) ? mu0[b0 + dd + i] : 0.f;
+  }
   for (long r0 = r_begin; r0 < r_end; r0 += BK) {
     const bool k_ok = (r0 + kk) < r_end;
     const T* row = X + (r0 + kk) * (long)D;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      As[kk][dd + i] = (k_ok && (a0 + dd + i) < D) ? to_f32<T>(row[a0 + dd + i]) : 0.f;
-      Bs[kk][dd + i] = (k_ok && (b0 + dd + i) < D) ? to_f32<T>(row[b0 + dd + i]) : 0.f;
+      As[kk][dd + i] = (k_ok && (a0 + dd + i) < D) ? to_f32<T>(row[a0 + dd + i]) - ma[i] : 0.f;
+      Bs[kk][dd + i] = (k_ok && (b0 + dd + i) < D) ? to_f32<T>(row[b0 + dd + i]) - mb[i] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -341,8 +347,12 @@ token_gram_partial_kernel(const T* __restrict__ X, long rows, int D, long rows_p
 
 // Folds the slices (fixed order) and mirrors the upper tiles into the lower triangle.
 // `tile` is the granularity at which the producer skipped the lower triangle.
+// mu0 / dsum / coef (tensor-core path, nullable): the producer accumulated  Gs = sum x x^T - Mc mu0 mu0^T;
+// the Gram of the shifted tokens is  G' = Gs + (Mc - M) mu0 mu0^T - mu0 d^T - d mu0^T  with d = sum (x - mu0)
+// and coef = Mc - M (|coef| < one stage of rows): three small terms, no cancellation.
 __global__ void gram_reduce_kernel(const float* __restrict__ partial, int slices, int D, int tile,
-                                   float* __restrict__ gram, float beta) {
+                                   float* __restrict__ gram, float beta, const float* __restrict__ mu0,
+                                   const float* __restrict__ dsum, float coef) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)D * D) return;
   int a = idx / D, b = idx % D;
@@ -350,21 +360,30 @@ __global__ void gram_reduce_kernel(const float* __restrict__ partial, int slices
   if (ta > tb) { const int s = a; a = b; b = s; }
   float sum = 0.f;
   for (int s = 0; s < slices; ++s) sum += partial[(long)s * D * D + (long)a * D + b];
+  if (mu0) {                                             // evaluated on (min, max) so that G'[a][b] == G'[b][a] bitwise
+    const int lo = min(a, b), hi = max(a, b);
+    sum += fmaf(coef * mu0[lo], mu0[hi], -fmaf(mu0[lo], dsum[hi], dsum[lo] * mu0[hi]));
+  }
   gram[idx] = sum + (beta != 0.f ? beta * gram[idx] : 0.f);
 }
 
 // Column sums: one block per 32-column group, rows strided over blockIdx.y, then a
 // deterministic second pass.
+// mu0 (nullable): the sums are taken of x - mu0 (each term exact in fp32 for bf16 tokens and a bf16 shift), so
+// that they stay small next to M mu0 and keep their relative accuracy (see the Gram entry points).
 template <typename T>
 __global__ void colsum_partial_kernel(const T* __restrict__ X, long rows, int D,
-                                      long rows_per_slice, float* __restrict__ partial) {
+                                      long rows_per_slice, float* __restrict__ partial,
+                                      const float* __restrict__ mu0) {
   const int d = blockIdx.x * 32 + (threadIdx.x & 31);
   const int sub = threadIdx.x >> 5;  // 8 row lanes
   const long r_begin = (long)blockIdx.y * rows_per_slice;
   const long r_end = min(rows, r_begin + rows_per_slice);
   float s = 0.f;
-  if (d < D)
-    for (long r = r_begin + sub; r < r_end; r += 8) s += to_f32<T>(X[r * D + d]);
+  if (d < D) {
+    const float m = mu0 ? mu0[d] : 0.f;
+    for (long r = r_begin + sub; r < r_end; r += 8) s += to_f32<T>(X[r * D + d]) - m;
+  }
   __shared__ float red[8][33];
   red[sub][threadIdx.x & 31] = s;
   __syncthreads();
@@ -380,13 +399,17 @@ __global__ void colsum_partial_kernel(const T* __restrict__ X, long rows, int D,
 // flight each -- an HBM-speed pass (the scalar kernel above reached 1.1 TB/s of 6.5).
 __global__ void __launch_bounds__(256)
 colsum_partial_bf16x8_kernel(const __nv_bfloat16* __restrict__ X, long rows, int D,
-                             long rows_per_slice, float* __restrict__ partial) {
+                             long rows_per_slice, float* __restrict__ partial,
+                             const float* __restrict__ mu0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = (blockIdx.x * 32 + lane) * 8;
   const long r_begin = (long)blockIdx.y * rows_per_slice;
   const long r_end = min(rows, r_begin + rows_per_slice);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c0 < D) {
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = mu0 ? mu0[c0 + i] : 0.f;
     long r = r_begin + warp;
     for (; r + 24 < r_end; r += 32) {
       float v[4][8];
@@ -395,13 +418,13 @@ colsum_partial_bf16x8_kernel(const __nv_bfloat16* __restrict__ X, long rows, int
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += v[u][i];
+        for (int i = 0; i < 8; ++i) acc[i] += v[u][i] - m[i];
     }
     for (; r < r_end; r += 8) {
       float v[8];
       load8(X + r * D + c0, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      for (int i = 0; i < 8; ++i) acc[i] += v[i] - m[i];
     }
   }
   __shared__ float red[8][256 + 8];
@@ -502,16 +525,16 @@ static int launch_sgemm(int a_dtype, int M, int N, int K, const void* A, int lda
 
 // Host-side helpers shared with gram_tc.cu (declared in common.cuh).
 int launch_gram_reduce(const float* partial, int slices, int D, int tile, float* gram,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* mu0, const float* dsum, float coef) {
   const long total = (long)D * D;
   gram_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, slices, D, tile, gram,
-                                                                      0.f);
+                                                                      0.f, mu0, dsum, coef);
   BASD_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial, float* out,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* mu0) {
   int cs = (int)((rows + 4095) / 4096);
   if (cs > 64) cs = 64;
   if (cs < 1) cs = 1;
@@ -522,7 +545,7 @@ int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial, flo
     const long per = (rows + cs - 1) / cs;
     dim3 vgrid((D + 255) / 256, cs);
     colsum_partial_bf16x8_kernel<<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)tokens, rows, D, per,
-                                                        partial);
+                                                        partial, mu0);
     colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(partial, cs, D, out);
     BASD_LAUNCH_CHECK();
     return 0;
@@ -530,7 +553,7 @@ int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial, flo
   const long per = (rows + cs - 1) / cs;
   dim3 cgrid((D + 31) / 32, cs);
   colsum_partial_kernel<__nv_bfloat16><<<cgrid, 256, 0, st>>>((const __nv_bfloat16*)tokens, rows, D,
-                                                              per, partial);
+                                                              per, partial, mu0);
   colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(partial, cs, D, out);
   BASD_LAUNCH_CHECK();
   return 0;
@@ -567,9 +590,11 @@ extern "C" long basd_token_gram_simt_workspace_floats(long rows, int D) {
   return slices * ((long)D * D + D);
 }
 
-// gram[D*D] = X^T X, colsum[D] = X^T 1 for X = tokens viewed as (rows, D).
-extern "C" int basd_token_gram_simt(const void* tokens, int dtype, long rows, int D, float* gram,
-                                    float* colsum, float* workspace, void* stream) {
+// gram[D*D] = X'^T X', colsum[D] = X'^T 1 for X' = tokens - 1 mu0^T viewed as (rows, D); mu0 (D floats,
+// nullable = no shift) is subtracted while the operands are staged (exact in fp32 for bf16 tokens).
+// colsum may be null (skipped).
+extern "C" int basd_token_gram_simt(const void* tokens, int dtype, long rows, int D, const float* mu0,
+                                    float* gram, float* colsum, float* workspace, void* stream) {
   using namespace basd;
   cudaStream_t st = (cudaStream_t)stream;
   long slices = (rows + 2047) / 2048;
@@ -584,19 +609,21 @@ extern "C" int basd_token_gram_simt(const void* tokens, int dtype, long rows, in
   dim3 cgrid((D + 31) / 32, (unsigned)slices);
   if (dtype == BASD_DTYPE_BF16) {
     token_gram_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
-        (const __nv_bfloat16*)tokens, rows, D, per, part_g);
-    colsum_partial_kernel<__nv_bfloat16><<<cgrid, 256, 0, st>>>((const __nv_bfloat16*)tokens, rows,
-                                                                D, per, part_c);
+        (const __nv_bfloat16*)tokens, rows, D, per, part_g, mu0);
+    if (colsum)
+      colsum_partial_kernel<__nv_bfloat16><<<cgrid, 256, 0, st>>>((const __nv_bfloat16*)tokens, rows,
+                                                                  D, per, part_c, mu0);
   } else {
     token_gram_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)tokens, rows, D, per,
-                                                           part_g);
-    colsum_partial_kernel<float><<<cgrid, 256, 0, st>>>((const float*)tokens, rows, D, per, part_c);
+                                                           part_g, mu0);
+    if (colsum)
+      colsum_partial_kernel<float><<<cgrid, 256, 0, st>>>((const float*)tokens, rows, D, per, part_c, mu0);
   }
   BASD_LAUNCH_CHECK();
   const long total = (long)D * D;
   gram_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(part_g, (int)slices, D, BM,
-                                                                      gram, 0.f);
-  colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(part_c, (int)slices, D, colsum);
+                                                                      gram, 0.f, nullptr, nullptr, 0.f);
+  if (colsum) colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(part_c, (int)slices, D, colsum);
   BASD_LAUNCH_CHECK();
   return 0;
 }

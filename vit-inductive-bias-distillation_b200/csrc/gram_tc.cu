@@ -13,6 +13,18 @@
 // A small deterministic reduce (gram_reduce_kernel) folds the slices and mirrors the tiles.
 // bf16 x bf16 products are exact in fp32, so the statistic equals the fp32 SIMT path up to
 // accumulation order (reference: `features.T @ features`, layer_selector.py:13).
+//
+// Mean shift.  The selector needs the CENTRED covariance; token means are large (|mu|^2 >> the eigenvalues
+// of interest), and the tensor-core accumulators carry a truncation bias proportional to what they hold:
+// ~3e-6 relative over the 2,090 rows a CTA sums at C2, i.e. 3e-6 M |mu|^2 -- more than the eigenvalue gap at
+// the Marchenko-Pastur rank boundary once |mu|^2 ~ 100 lambda_max (measured at B = 256: the centred matrix
+// came out indefinite and the selector gradient had cosine 0.87 against autograd through the reference).
+// Centring the TOKENS first would round x - mu to bf16 (noise 2^-9 per entry whose cross terms with x do
+// not average out at small batches: C4, B = 8 lost its parity to it).  Instead the tokens stay exactly as
+// they are and every 64-row stage is preceded by ONE extra UMMA on a constant 16-row operand whose first
+// row is 8 mu0 (mu0 = a rough mean, bf16 exact) with the B operand negated: it subtracts 64 mu0 mu0^T
+// exactly, so the accumulator never holds more than one stage of the mean term.  The result
+// Gs = sum x x^T - Mc mu0 mu0^T is converted to the Gram of the shifted tokens by the reduce kernel.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -26,7 +38,10 @@ constexpr int STAGES = 6;
 constexpr int BOX_BYTES = BK * 128;       // one TMA box: 64 bf16 columns x BK rows
 constexpr int OPERAND_BYTES = 2 * BOX_BYTES;
 constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MU_ROWS = 16;               // one UMMA K step: row 0 = 8 mu0, rows 1..15 = 0
+constexpr int MU_BOX_BYTES = MU_ROWS * 128;
+constexpr int MU_BYTES = 4 * MU_BOX_BYTES;        // A (two 64-column boxes) + B (two boxes)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + MU_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TMEM_COLS = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -83,10 +98,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 //   bits [16,30) leading byte offset >> 4 : distance between 64-element MN chunks
 //   bits [32,46) stride byte offset  >> 4 : distance between groups of 8 K rows (8 x 128 B)
 //   bits [46,48) version = 1 (Blackwell);  bits [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int box_bytes = BOX_BYTES) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
-  d |= static_cast<uint64_t>((BOX_BYTES >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((box_bytes >> 4) & 0x3fff) << 16;
   d |= static_cast<uint64_t>((1024 >> 4) & 0x3fff) << 32;
   d |= 1ull << 46;
   d |= 2ull << 61;
@@ -98,16 +113,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                            ((TILE >> 3) << 17) | ((TILE >> 4) << 24);
 
+constexpr uint32_t IDESC_NEG_B = IDESC | (1u << 14);      // bit 14: negate B
+
+// mu tile (16 x D bf16, row-major): row 0 = 8 mu0, rows 1..15 = 0
+__global__ void mu_tile_kernel(const float* __restrict__ mu0, int D, __nv_bfloat16* __restrict__ tile) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= MU_ROWS * D) return;
+  tile[idx] = __float2bfloat16(idx < D ? 8.f * mu0[idx] : 0.f);
+}
+
 __global__ void __launch_bounds__(192, 1)
-token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ partial, int D,
-                     long rows, long rows_per_slice) {
+token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_mu,
+                     int use_mu, float* __restrict__ partial, int D, long rows, long rows_per_slice) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* mu_smem = smem + STAGES * STAGE_BYTES;         // 1024-byte aligned (swizzle atom)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(mu_smem + MU_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* mu_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mu_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = D / TILE;
@@ -121,6 +147,7 @@ token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(mu_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
   }
@@ -138,6 +165,13 @@ token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict
 
   if (warp == 0) {
     if (lane == 0) {                                  // ===== TMA producer =====
+      if (use_mu && num_kb > 0) {                      // the constant correction operands, once
+        mbar_expect_tx(mu_bar, MU_BYTES);
+        tma_load_2d(mu_smem, &tmap_mu, mu_bar, ti * TILE, 0);
+        tma_load_2d(mu_smem + MU_BOX_BYTES, &tmap_mu, mu_bar, ti * TILE + 64, 0);
+        tma_load_2d(mu_smem + 2 * MU_BOX_BYTES, &tmap_mu, mu_bar, tj * TILE, 0);
+        tma_load_2d(mu_smem + 3 * MU_BOX_BYTES, &tmap_mu, mu_bar, tj * TILE + 64, 0);
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -154,6 +188,13 @@ token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict
     }
   } else if (warp == 1) {
     if (lane == 0) {                                  // ===== MMA issuer (one thread) =====
+      uint64_t dmu_a = 0, dmu_b = 0;
+      if (use_mu && num_kb > 0) {
+        mbar_wait(mu_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        dmu_a = make_desc(smem_u32(mu_smem), MU_BOX_BYTES);
+        dmu_b = make_desc(smem_u32(mu_smem + 2 * MU_BOX_BYTES), MU_BOX_BYTES);
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -161,11 +202,13 @@ token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b = a + OPERAND_BYTES;
+        // -(8 mu0)(8 mu0)^T = -BK mu0 mu0^T first: the accumulator never holds more than one stage of it
+        if (use_mu) umma_bf16(tmem_base, dmu_a, dmu_b, IDESC_NEG_B, kb > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {           // UMMA K = 16 rows = 2 x (8 rows x 128 B)
           const uint64_t da = make_desc(a + k * 2048);
           const uint64_t db = make_desc(b + k * 2048);
-          umma_bf16(tmem_base, da, db, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, da, db, IDESC, (use_mu || kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);                   // frees the smem slot when the MMAs retire
       }
@@ -248,40 +291,67 @@ static int plan_slices(long rows, int D) {
 
 extern "C" long basd_token_gram_tc_workspace_bytes(long rows, int D) {
   const int slices = basd::tc::plan_slices(rows, D);
-  return (static_cast<long>(slices) * D * D + static_cast<long>(64) * D) * sizeof(float);
+  return (static_cast<long>(slices) * D * D + static_cast<long>(64) * D + 2L * D) * sizeof(float) +
+         static_cast<long>(basd::tc::MU_ROWS) * D * 2 + 256;
 }
 
-// tokens: (rows x D) bf16, D % 128 == 0, 16-byte aligned. gram (D x D) and colsum (D) fp32.
-extern "C" int basd_token_gram_tc(const void* tokens, long rows, int D, float* gram, float* colsum,
-                                  void* workspace, void* stream) {
+static CUresult encode_2d(basd::tc::EncodeTiledFn encode, CUtensorMap* map, const void* base, int D, long rows,
+                          int box_rows) {
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(D) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estride[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// tokens: (rows x D) bf16, D % 128 == 0, 16-byte aligned.  mu0 (D floats, bf16-representable values,
+// nullable = no shift).  gram (D x D) = X'^T X' and colsum (D, nullable = skipped) = X'^T 1 of the shifted
+// tokens X' = X - 1 mu0^T, fp32; the tokens themselves enter the tensor cores unchanged (see the header
+// comment).  With a shift the column sums are needed internally: colsum must not be null then.
+extern "C" int basd_token_gram_tc(const void* tokens, long rows, int D, const float* mu0, float* gram,
+                                  float* colsum, void* workspace, void* stream) {
   using namespace basd;
   using namespace basd::tc;
   if (D % TILE != 0 || rows <= 0) return -9;
+  if (mu0 && !colsum) return -9;
   cudaStream_t st = (cudaStream_t)stream;
   EncodeTiledFn encode = encode_fn();
   if (!encode) return -10;
-  CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(D) * 2};
-  const cuuint32_t box[2] = {64, BK};
-  const cuuint32_t estride[2] = {1, 1};
-  const CUresult rc = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(tokens),
-                             gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS) return -11;
   const int slices = plan_slices(rows, D);
   long per = (rows + slices - 1) / slices;
   per = (per + BK - 1) / BK * BK;
   const int tiles = D / TILE;
   float* part_g = static_cast<float*>(workspace);
   float* part_c = part_g + static_cast<long>(slices) * D * D;
+  __nv_bfloat16* mu_tile = reinterpret_cast<__nv_bfloat16*>(
+      (reinterpret_cast<uintptr_t>(part_c + static_cast<long>(64) * D + 2L * D) + 255) & ~static_cast<uintptr_t>(255));
+  CUtensorMap tmap, tmap_mu;
+  if (encode_2d(encode, &tmap, tokens, D, rows, BK) != CUDA_SUCCESS) return -11;
+  long corrected = 0;                                   // Mc: rows' worth of mu0 mu0^T the kernel subtracts
+  if (mu0) {
+    mu_tile_kernel<<<(MU_ROWS * D + 255) / 256, 256, 0, st>>>(mu0, D, mu_tile);
+    BASD_LAUNCH_CHECK();
+    if (encode_2d(encode, &tmap_mu, mu_tile, D, MU_ROWS, MU_ROWS) != CUDA_SUCCESS) return -11;
+    for (int s = 0; s < slices; ++s) {
+      const long k_begin = static_cast<long>(s) * per, k_end = rows < k_begin + per ? rows : k_begin + per;
+      if (k_end > k_begin) corrected += (k_end - k_begin + BK - 1) / BK * BK;
+    }
+    // column sums of the shifted tokens first: the reduce below needs them
+    if (int e = launch_colsum_bf16(tokens, rows, D, part_c, colsum, st, mu0)) return e;
+  } else {
+    tmap_mu = tmap;
+  }
   BASD_CUDA(cudaFuncSetAttribute(token_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SMEM_BYTES));
   dim3 grid(tiles * (tiles + 1) / 2, slices);
-  token_gram_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tmap, part_g, D, rows, per);
+  token_gram_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tmap, tmap_mu, mu0 ? 1 : 0, part_g, D, rows, per);
   BASD_LAUNCH_CHECK();
-  if (int e = launch_gram_reduce(part_g, slices, D, TILE, gram, st)) return e;
+  if (int e = launch_gram_reduce(part_g, slices, D, TILE, gram, st, mu0, colsum,
+                                 static_cast<float>(corrected - rows)))
+    return e;
+  if (mu0 || !colsum) return 0;
   // column sums (HBM-bound, one extra pass over the tokens)
   return launch_colsum_bf16(tokens, rows, D, part_c, colsum, st);
 }

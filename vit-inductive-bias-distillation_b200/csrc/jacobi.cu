@@ -399,7 +399,7 @@ pivoted_cholesky_left4_cluster_kernel(const float* __restrict__ Kbase, int n, in
 template <int NV, int R, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 jacobi_rows_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                           const int* __restrict__ dims, float tol, int max_sweeps,
+                           const int* __restrict__ dims, float tol, float stop2, int max_sweeps,
                            int* __restrict__ sweeps_out, int dim_lo, int dim_hi) {
   cg::cluster_group cluster = cg::this_cluster();
   const int csize = cluster.num_blocks(), crank = cluster.block_rank();
@@ -505,7 +505,7 @@ jacobi_rows_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long
     cluster.sync();
     const float all_worst = __int_as_float(*flag0);
     cluster.sync();                                      // everyone has read before rank 0 resets
-    if (all_worst < tol) { ++sweep; break; }             // quadratic convergence: see grouped kernel
+    if (all_worst < stop2) { ++sweep; break; }             // quadratic convergence: see grouped kernel
   }
   if (sweeps_out && crank == 0 && tid == 0) sweeps_out[prob] = sweep;
 }
@@ -606,7 +606,7 @@ static int sm_count() {
 
 template <int NV, int R, int MAXT>
 static int launch_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
-                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st,
+                          float tol, float stop2, int max_sweeps, int* sweeps_out, cudaStream_t st,
                           int dim_lo = 0, int dim_hi = 1 << 30) {
   int csize = 8;
   while (csize > 1 && (long)batch * csize > sm_count()) csize >>= 1;
@@ -625,7 +625,7 @@ static int launch_cluster(float* G, int n, int m, int ld, long stride, int batch
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_cluster_kernel<NV, R, MAXT>, G, n, m, ld, stride,
-                               dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi));
+                               dims, tol, stop2, max_sweeps, sweeps_out, dim_lo, dim_hi));
   return 0;
 }
 
@@ -718,7 +718,7 @@ extern "C" int basd_pivoted_cholesky(float* K, int n, int ld, long stride_k, flo
 
 namespace basd {
 // jacobi_oe8.cu: the same sweep with one problem split over a cluster of 4 CTAs, three CTAs per SM
-int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
+int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol, float stop2,
                             int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
                             int dim_hi, int rows_only = 0);
 
@@ -731,15 +731,32 @@ static bool few_problems(int batch) { return (long)batch * 4 <= 2L * sm_count();
 
 // Orthogonalises the rows of each (n x m) row-major matrix in place. ld % 4 == 0 and
 // 16-byte aligned bases are required (128-bit row accesses).
-extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,
-                                        const int* dims, float tol, int max_sweeps, int* sweeps_out,
-                                        int* rot_out, void* stream);
+//
+// Two thresholds on the cosine between two rows: a pair is rotated while |cos| > tol, and the sweeps stop
+// after one in which every rotated pair had |cos| < stop_cos.  stop_cos = sqrt(tol) relies on the quadratic
+// convergence of the sweep (what is left after such a sweep is O(stop_cos^2) = tol) and is what the
+// legacy entry points use: right for singular values, polar factors and well-separated spectra.  It is
+// NOT enough for eigenvectors of a dense spectrum: two rows whose norms differ by a relative gap g keep
+// mixing by an angle ~ cos / g, and with 50,176 token rows the selector Grams have g ~ 1e-3 at the
+// Marchenko-Pastur rank boundary (measured at C2, B = 256: selector gradient cosine 0.87 with
+// stop_cos = 1e-3) -- sym_eig passes a tighter stop_cos through basd_jacobi_rows_ex.
+static int jacobi_dispatch(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                           const int* row_dims, float tol, float stop2, int max_sweeps, int* sweeps_out,
+                           int* rot_out, void* stream);
+
+extern "C" int basd_jacobi_rows_ex(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                                   const int* row_dims, float tol, float stop_cos, int max_sweeps,
+                                   int* sweeps_out, int* rot_out, void* stream) {
+  if (dims && row_dims) return -5;
+  return jacobi_dispatch(G, n, m, ld, stride, batch, dims, row_dims, tol, stop_cos * stop_cos, max_sweeps,
+                         sweeps_out, rot_out, stream);
+}
 
 extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int batch,
                                 const int* dims, float tol, int max_sweeps, int* sweeps_out,
                                 void* stream) {
-  return basd_jacobi_rows_counted(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out,
-                                  nullptr, stream);
+  return jacobi_dispatch(G, n, m, ld, stride, batch, dims, nullptr, tol, tol, max_sweeps, sweeps_out, nullptr,
+                         stream);
 }
 
 // Rank-deficient factor products (G = F_q^T F_p with a pivoted-Cholesky F_q of rank r): only the
@@ -749,39 +766,43 @@ extern "C" int basd_jacobi_rows(float* G, int n, int m, int ld, long stride, int
 extern "C" int basd_jacobi_rows_ranked(float* G, int n, int m, int ld, long stride, int batch,
                                        const int* row_dims, float tol, int max_sweeps,
                                        int* sweeps_out, int* rot_out, void* stream) {
-  using namespace basd;
-  if (batch <= 0 || n <= 0) return 0;
-  if ((ld & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(G) & 15)) return -3;
-  if (row_dims && n <= 256 && m <= 256) {
-    const int e = launch_jacobi_oe8(G, n, m, ld, stride, batch, row_dims, tol, max_sweeps, sweeps_out,
-                                    (cudaStream_t)stream, 0, 1 << 30, rot_out, 1);
-    if (e != -100) return e;
-  }
-  return basd_jacobi_rows_counted(G, n, m, ld, stride, batch, nullptr, tol, max_sweeps, sweeps_out,
-                                  rot_out, stream);
+  return jacobi_dispatch(G, n, m, ld, stride, batch, nullptr, row_dims, tol, tol, max_sweeps, sweeps_out,
+                         rot_out, stream);
 }
 
-// Same, additionally accumulating into rot_out[problem] the number of plane rotations applied
-// (bench.py's roofline leg; only the register-resident kernels count, others leave it untouched).
+// Same as basd_jacobi_rows, additionally accumulating into rot_out[problem] the number of plane rotations
+// applied (bench.py's roofline leg; only the register-resident kernels count, others leave it untouched).
+extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,
+                                        const int* dims, float tol, int max_sweeps, int* sweeps_out,
+                                        int* rot_out, void* stream) {
+  return jacobi_dispatch(G, n, m, ld, stride, batch, dims, nullptr, tol, tol, max_sweeps, sweeps_out, rot_out,
+                         stream);
+}
+
 // Routes: rows and columns <= 256 -> one CTA per problem, eight rows per 16-lane group in registers
 // (jacobi_oe8.cu), or four CTAs per problem when the launch has few problems; square problems with a
 // device-side active size (dims) in a wider allocation -> the same kernels through their size window
 // [0, 200], the rest on the cluster kernel; up to 768 x 768 -> the eight-row layout spread over a
-// thread-block cluster; larger -> the L2-resident cluster kernel below.
-extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long stride, int batch,
-                                        const int* dims, float tol, int max_sweeps, int* sweeps_out,
-                                        int* rot_out, void* stream) {
+// thread-block cluster; larger -> the L2-resident cluster kernel above.
+static int jacobi_dispatch(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
+                           const int* row_dims, float tol, float stop2, int max_sweeps, int* sweeps_out,
+                           int* rot_out, void* stream) {
   using namespace basd;
   if (batch <= 0 || n <= 0) return 0;
   if ((ld & 3) || (stride & 3) || (reinterpret_cast<uintptr_t>(G) & 15)) return -3;
+  if (row_dims && n <= 256 && m <= 256) {
+    const int e = launch_jacobi_oe8(G, n, m, ld, stride, batch, row_dims, tol, stop2, max_sweeps, sweeps_out,
+                                    (cudaStream_t)stream, 0, 1 << 30, rot_out, 1);
+    if (e != -100) return e;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 256 && m <= 256) {
     int e = -100;
     if (few_problems(batch))
-      e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, rot_out, 4, 0,
+      e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, rot_out, 4, 0,
                                   1 << 30);
     if (e == -100)
-      e = launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, 0, 1 << 30, rot_out);
+      e = launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, 0, 1 << 30, rot_out);
     if (e != -100) return e;
   }
   int lo = 0;
@@ -789,15 +810,15 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
     constexpr int SMALL = 200;
     int e = -100;
     if (few_problems(batch))
-      e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, rot_out, 4, 0,
+      e = launch_jacobi_oe8_split(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, rot_out, 4, 0,
                                   SMALL);
     if (e == -100)
-      e = launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, 0, SMALL, rot_out);
+      e = launch_jacobi_oe8(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, 0, SMALL, rot_out);
     if (e == 0) lo = SMALL + 1;
     else if (e != -100) return e;
   }
   if ((m <= 384 || !dims) && m <= 768 && n <= 768) {
-    const int e = launch_jacobi_oe8_cluster(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
+    const int e = launch_jacobi_oe8_cluster(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps,
                                             sweeps_out, st, lo, 1 << 30, rot_out);
     if (e == 0) return 0;                                  // (-100 or a refused non-portable cluster: fall through)
     (void)cudaGetLastError();
@@ -805,21 +826,21 @@ extern "C" int basd_jacobi_rows_counted(float* G, int n, int m, int ld, long str
   // wider allocations with a device-side active size (C4: k ~ 366 of 768): the problems whose
   // active size fits take the cluster kernel through its size window, the rest fall through
   if (dims && n == m && m > 384 && m <= 768 && lo <= 384) {
-    const int e = launch_jacobi_oe8_cluster(G, n, m, ld, stride, batch, dims, tol, max_sweeps,
+    const int e = launch_jacobi_oe8_cluster(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps,
                                             sweeps_out, st, lo, 384, rot_out);
     if (e == 0) lo = 385;
     else if (e != -100) return e;
   }
   const int quads = (m + 3) / 4;
   switch ((quads + 31) / 32) {
-    case 1: return launch_cluster<1, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
-    case 2: return launch_cluster<2, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
-    case 3: return launch_cluster<3, 2, 768>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
-    case 4: return launch_cluster<4, 1, 1024>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
+    case 1: return launch_cluster<1, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, lo);
+    case 2: return launch_cluster<2, 2, 1024>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, lo);
+    case 3: return launch_cluster<3, 2, 768>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, lo);
+    case 4: return launch_cluster<4, 1, 1024>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, lo);
     case 5: case 6:
-      return launch_cluster<6, 1, 512>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
+      return launch_cluster<6, 1, 512>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, lo);
     case 7: case 8:
-      return launch_cluster<8, 1, 512>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, lo);
+      return launch_cluster<8, 1, 512>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, lo);
     default: return -4;  // m > 1024 unsupported
   }
 }

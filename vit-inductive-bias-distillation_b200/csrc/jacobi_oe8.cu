@@ -278,7 +278,7 @@ __device__ __forceinline__ void sweep_steps(float (&r)[R - 1][NF], float& sn, fl
 template <int G, int NF>    // G lanes per group; NF floats per lane per row: columns lane + G j, j < NF
 __global__ void __launch_bounds__(G == 16 ? 512 : 896, 1)
 jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                       const int* __restrict__ dims, float tol, int max_sweeps,
+                       const int* __restrict__ dims, float tol, float stop2, int max_sweeps,
                        int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
                        int* __restrict__ rot_out, int rows_only) {
   extern __shared__ __align__(16) float smem[];
@@ -375,7 +375,7 @@ jacobi_rows_oe8_kernel(float* __restrict__ Gbase, int n, int m, int ld, long str
       sweep_steps<G, NF, false>(r, sn, sd, xs, slot, right, my_row, right_row, gl, cnt, cross_ok, nn, tol2, zero_thr,
                                 worst, nrot);
     worst = block_max(worst, red_scratch);
-    if (worst < tol) { ++sweep; break; }
+    if (worst < stop2) { ++sweep; break; }
   }
   {
     const float d0 = (nn >= 2 && sweep) ? xs[slot].y : 1.f;
@@ -447,7 +447,7 @@ __device__ __forceinline__ void angle_pass_ptr(float g_own, float& sn, float& sd
 template <int G, int NF>
 __device__ __forceinline__ void
 jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                             const int* __restrict__ dims, float tol, int max_sweeps,
+                             const int* __restrict__ dims, float tol, float stop2, int max_sweeps,
                              int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
                              int* __restrict__ rot_out) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -598,7 +598,7 @@ jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, lo
     }
     const float all_worst = wide_max(worst, 1);
     cluster.sync();                                      // everyone has read the flags before rank 0 resets them
-    if (all_worst < tol) { ++sweep; break; }
+    if (all_worst < stop2) { ++sweep; break; }
   }
   {
     const float d0 = (nn >= 2 && sweep) ? xs_my->y : 1.f;
@@ -632,10 +632,10 @@ jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, lo
 template <int G, int NF>
 __global__ void __launch_bounds__(192, 1)
 jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                               const int* __restrict__ dims, float tol, int max_sweeps,
+                               const int* __restrict__ dims, float tol, float stop2, int max_sweeps,
                                int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
                                int* __restrict__ rot_out) {
-  jacobi_rows_oe8_cluster_body<G, NF>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi,
+  jacobi_rows_oe8_cluster_body<G, NF>(Gbase, n, m, ld, stride, dims, tol, stop2, max_sweeps, sweeps_out, dim_lo, dim_hi,
                                       rot_out);
 }
 
@@ -648,17 +648,17 @@ jacobi_rows_oe8_cluster_kernel(float* __restrict__ Gbase, int n, int m, int ld, 
 template <int G, int NF, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 jacobi_rows_oe8_split_kernel(float* __restrict__ Gbase, int n, int m, int ld, long stride,
-                             const int* __restrict__ dims, float tol, int max_sweeps,
+                             const int* __restrict__ dims, float tol, float stop2, int max_sweeps,
                              int* __restrict__ sweeps_out, int dim_lo, int dim_hi,
                              int* __restrict__ rot_out) {
-  jacobi_rows_oe8_cluster_body<G, NF>(Gbase, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi,
+  jacobi_rows_oe8_cluster_body<G, NF>(Gbase, n, m, ld, stride, dims, tol, stop2, max_sweeps, sweeps_out, dim_lo, dim_hi,
                                       rot_out);
 }
 
 // MAXT / MINB: 128 threads x 3 CTAs per SM (<= 8 groups per CTA: 168 registers, no spills at 13 floats
 // per row piece).
 template <int NF, int MAXT, int MINB>
-static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
+static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol, float stop2,
                         int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
                         int dim_hi) {
   constexpr int G = 16;
@@ -684,14 +684,14 @@ static int launch_split(float* Gm, int n, int m, int ld, long stride, int batch,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BASD_CUDA(cudaLaunchKernelEx(&cfg, kernel, Gm, n, m, ld, stride, dims, tol, max_sweeps, sweeps_out, dim_lo, dim_hi,
+  BASD_CUDA(cudaLaunchKernelEx(&cfg, kernel, Gm, n, m, ld, stride, dims, tol, stop2, max_sweeps, sweeps_out, dim_lo, dim_hi,
                                rot_out));
   return 0;
 }
 
 template <int G, int NF>
 static int launch_cluster(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims,
-                          float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                          float tol, float stop2, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                           int dim_hi, int* rot_out) {
   int GPC_MAX = 192 / G;                                  // 192 threads: up to 255 registers each
   const int cap = (dims && dim_hi < n) ? dim_hi : n;
@@ -734,13 +734,13 @@ static int launch_cluster(float* Gm, int n, int m, int ld, long stride, int batc
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_oe8_cluster_kernel<G, NF>, Gm, n, m, ld, stride, dims, tol,
+  BASD_CUDA(cudaLaunchKernelEx(&cfg, jacobi_rows_oe8_cluster_kernel<G, NF>, Gm, n, m, ld, stride, dims, tol, stop2,
                                max_sweeps, sweeps_out, dim_lo, dim_hi, rot_out));
   return 0;
 }
 
 template <int G, int NF>
-static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
+static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const int* dims, float tol, float stop2,
                   int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo, int dim_hi,
                   int* rot_out, int rows_only) {
   const int cap = (dims && !rows_only && dim_hi < n) ? dim_hi : n;
@@ -751,7 +751,7 @@ static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const
   const size_t dyn = (nslots * row_pitch<G, NF>() + 2 * nslots + 4) * sizeof(float);
   BASD_CUDA(cudaFuncSetAttribute(jacobi_rows_oe8_kernel<G, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)dyn));
-  jacobi_rows_oe8_kernel<G, NF><<<batch, threads, dyn, st>>>(Gm, n, m, ld, stride, dims, tol, max_sweeps,
+  jacobi_rows_oe8_kernel<G, NF><<<batch, threads, dyn, st>>>(Gm, n, m, ld, stride, dims, tol, stop2, max_sweeps,
                                                           sweeps_out, dim_lo, dim_hi, rot_out, rows_only);
   BASD_LAUNCH_CHECK();
   return 0;
@@ -762,13 +762,13 @@ static int launch(float* Gm, int n, int m, int ld, long stride, int batch, const
 // Problems with at most 256 active rows and 256 active columns (the per-sample Procrustes SVDs
 // and the k x k principal-angle SVDs).  Returns -100 when the shape does not fit.
 int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
-                      float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                      float tol, float stop2, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                       int dim_hi, int* rot_out, int rows_only) {
   const int cap_n = (dims && !rows_only && dim_hi < n) ? dim_hi : n;
   const int cap_m = (dims && !rows_only && dim_hi < m) ? dim_hi : m;
   if (cap_n > 256 || cap_m > 256) return -100;          // 16 warps x 128 registers per CTA
 #define BASD_OE8(NF) \
-  return oe8::launch<16, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out, rows_only)
+  return oe8::launch<16, NF>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out, rows_only)
   if (cap_m <= 64) BASD_OE8(4);
   if (cap_m <= 96) BASD_OE8(6);
   if (cap_m <= 128) BASD_OE8(8);
@@ -783,14 +783,14 @@ int launch_jacobi_oe8(float* G, int n, int m, int ld, long stride, int batch, co
 // Split of the small problems over 4 CTAs (see jacobi_rows_oe8_split_kernel), for launches with few
 // problems: full problems (dims == null) or square problems with a device-side active size inside
 // [dim_lo, dim_hi].  Returns -100 when the shape does not fit.
-int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol,
+int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int batch, const int* dims, float tol, float stop2,
                             int max_sweeps, int* sweeps_out, cudaStream_t st, int* rot_out, int csize, int dim_lo,
                             int dim_hi, int rows_only) {
   const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
   const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
   if (cap_n > 256 || cap_m > 208 || csize != 4 || rows_only) return -100;
 #define BASD_OE8S(NF)                                                                                         \
-  return oe8::launch_split<NF, 128, 3>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, rot_out, \
+  return oe8::launch_split<NF, 128, 3>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, rot_out, \
                                        csize, dim_lo, dim_hi)
   if (cap_m <= 128) BASD_OE8S(8);
   if (cap_m <= 192) BASD_OE8S(12);
@@ -802,13 +802,13 @@ int launch_jacobi_oe8_split(float* G, int n, int m, int ld, long stride, int bat
 // clusters), up to 768 with 32-lane groups (cluster size 16 for more than 384 rows).
 // Returns -100 when the shape does not fit.
 int launch_jacobi_oe8_cluster(float* G, int n, int m, int ld, long stride, int batch, const int* dims,
-                              float tol, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
+                              float tol, float stop2, int max_sweeps, int* sweeps_out, cudaStream_t st, int dim_lo,
                               int dim_hi, int* rot_out) {
   const int cap_n = (dims && dim_hi < n) ? dim_hi : n;
   const int cap_m = (dims && dim_hi < m) ? dim_hi : m;
   if (cap_n > 768 || cap_m > 768) return -100;
 #define BASD_OE8C(GG, NF) \
-  return oe8::launch_cluster<GG, NF>(G, n, m, ld, stride, batch, dims, tol, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
+  return oe8::launch_cluster<GG, NF>(G, n, m, ld, stride, batch, dims, tol, stop2, max_sweeps, sweeps_out, st, dim_lo, dim_hi, rot_out)
   // (321..384 columns on 32-lane groups with 12-float row pieces over 8-CTA clusters measured
   //  slower: 5.85 vs 4.55 ms for the 16 x 384^2 eigenproblems of C2)
   if (cap_m <= 256) BASD_OE8C(16, 16);

@@ -276,17 +276,42 @@ __global__ void symmetrize_add_kernel(const float* __restrict__ in, int D, float
   out[(long)prob * D * D + idx] = m[(long)i * D + j] + m[(long)j * D + i];
 }
 
+// K <- K + rel_shift * max(diag K) * I, one block per problem.  The eigenvectors of K + delta I are those
+// of K; the shift only keeps the pivoted Cholesky behind sym_eig away from noise-sized pivots when fp32
+// rounding has pushed the smallest eigenvalues of a nearly singular Gram to zero or below (a noise pivot
+// divides noise off-diagonals into an O(1) garbage column; cutting the factorisation early instead drops
+// up to (D - r) cut-sized pivots of mass, more than the eigenvalue gap at the rank boundary).
+__global__ void shift_diag_kernel(float* __restrict__ K, int D, float rel_shift) {
+  __shared__ float red[32];
+  float* k = K + (long)blockIdx.x * D * D;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) mx = fmaxf(mx, k[(long)i * D + i]);
+  mx = block_max(mx, red);
+  const float delta = rel_shift * mx;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) k[(long)i * D + i] += delta;
+}
+
 // ---- null-space completion (fewer token rows than dimensions, layer_selector.py:14-15 regime) ----
 // sym_eig leaves the eigenvector rows of a rank-deficient Gram beyond its rank r as zeros.  The thin-SVD
 // backward needs them: its (I - V V^T) term acts on exactly that complement.  P = I - V_r^T V_r is the
 // orthogonal projector onto it, and the pivoted Cholesky factor of a projector has orthonormal columns
 // (P = L L^T and P^2 = P give L^T L = I), so rows 0..D-r-1 of LT are an orthonormal basis of the null space.
-__global__ void projector_complement_kernel(const float* __restrict__ vtv, int D, float* __restrict__ P) {
+// dims_out[problem] = D when rows are missing (trace of V^T V = number of unit rows < D), else 0: the
+// Cholesky launch that follows exits at once for complete bases (the common case costs four tiny launches).
+__global__ void projector_complement_kernel(const float* __restrict__ vtv, int D, float* __restrict__ P,
+                                            int* __restrict__ dims_out) {
+  __shared__ float red[32];
   const int prob = blockIdx.y;
+  const float* g = vtv + (long)prob * D * D;
+  if (blockIdx.x == 0) {
+    float tr = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) tr += g[(long)i * D + i];
+    tr = block_sum(tr, red);
+    if (threadIdx.x == 0) dims_out[prob] = ((float)D - tr > 0.5f) ? D : 0;
+  }
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)D * D) return;
   const int i = idx / D, j = idx % D;
-  const float* g = vtv + (long)prob * D * D;
   P[(long)prob * D * D + idx] = (i == j ? 1.f : 0.f) - 0.5f * (g[(long)i * D + j] + g[(long)j * D + i]);
 }
 
@@ -391,10 +416,18 @@ extern "C" int basd_omega_accumulate(const float* block, const float* lam_s, con
   return 0;
 }
 
-extern "C" int basd_projector_complement(const float* vtv, int D, float* P, int batch, void* stream) {
+extern "C" int basd_shift_diag(float* K, int D, float rel_shift, int batch, void* stream) {
+  if (batch <= 0) return 0;
+  shift_diag_kernel<<<batch, 256, 0, ST>>>(K, D, rel_shift);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int basd_projector_complement(const float* vtv, int D, float* P, int* dims_out, int batch,
+                                         void* stream) {
   if (batch <= 0) return 0;
   dim3 grid(blocks_for((long)D * D, 256), batch);
-  projector_complement_kernel<<<grid, 256, 0, ST>>>(vtv, D, P);
+  projector_complement_kernel<<<grid, 256, 0, ST>>>(vtv, D, P, dims_out);
   BASD_LAUNCH_CHECK();
   return 0;
 }
