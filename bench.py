@@ -42,26 +42,51 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, sm_max_mhz=1965.0, source="fallback")
 
 
-def bind_to_gpu_numa_node(index):
+ORIG_AFFINITY = os.sched_getaffinity(0)
+
+
+def _cpulist(text):
+    ids = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+    return ids
+
+
+def bind_to_gpu_numa_node(index, world=1):
     """Pins this process to the CPUs local to GPU `index` BEFORE any pinned host buffer is allocated,
     so that cudaHostAlloc places the staging pages on the GPU's own NUMA node (eight ranks streaming
     1.1 GB per step each through a remote socket is what broke the end-to-end scaling in round 1).
-    Returns a short description for the JSON line; a no-op when sysfs has no answer."""
+    sysfs first (numa_node / local_cpulist of the GPU's PCI device); where the platform hides that
+    (numa_node = -1) but exposes several nodes, ranks are dealt to the nodes in order (GPUs 0..W/2-1 on
+    the first socket is the usual board layout).  Returns a short description for the JSON line."""
+    info = {"numa_node": None}
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+    except OSError:
+        nodes = []
+    info["nodes_visible"] = len(nodes)
     try:
         prop = torch.cuda.get_device_properties(index)
         bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
-        base = f"/sys/bus/pci/devices/{bus}"
-        node = int(open(f"{base}/numa_node").read())
-        cpus = open(f"{base}/local_cpulist").read().strip()
-        ids = set()
-        for part in cpus.split(","):
-            lo, _, hi = part.partition("-")
-            ids.update(range(int(lo), int(hi or lo) + 1))
-        if ids:
-            os.sched_setaffinity(0, ids & os.sched_getaffinity(0) or ids)
-        return {"numa_node": node, "cpus": cpus}
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        ids = _cpulist(open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read())
+        how = "sysfs"
+        if node < 0 and len(nodes) > 1:
+            node = nodes[min(len(nodes) - 1, index * len(nodes) // max(1, world))]
+            ids = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+            how = "dealt by rank (platform reports numa_node -1)"
+        info.update(numa_node=node, how=how)
+        allowed = os.sched_getaffinity(0)
+        if node >= 0 and ids & allowed:
+            os.sched_setaffinity(0, ids & allowed)
+            info["cpus_bound"] = len(ids & allowed)
+        else:
+            info["cpus_bound"] = 0
     except Exception as exc:                                 # no sysfs entry, restricted cpuset, ...
-        return {"numa_node": None, "note": f"not bound ({type(exc).__name__})"}
+        info["note"] = f"not bound ({type(exc).__name__})"
+    return info
 
 
 def measured_traffic():
@@ -259,13 +284,19 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local)      # before the first pinned allocation
+    numa = bind_to_gpu_numa_node(local, world)      # before the first pinned allocation
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=300))
     parity = dp_parity(args, rank, world, device) if world > 1 and not args.no_dp_parity else None
     work = syn.scaled(syn.WORKLOADS[args.workload], args.batch)
     mod = build_module(work, device)
+    eager_mod = mod
+    if args.graph:                       # fwd+bwd replayed from one CUDA graph (single-GPU; see graphed.py)
+        if world > 1:
+            raise SystemExit("--graph is single-GPU only (the statistics all-reduces are not captured)")
+        from basd_b200.graphed import GraphedBASDLoss
+        mod = GraphedBASDLoss(mod)
     logits, targets, st, te, at = make_inputs(args, work, rank, device)
     st = {k: v.requires_grad_(True) for k, v in st.items()}
     logits.requires_grad_(True)
@@ -277,6 +308,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    launches_eager = 0
+    if args.graph:                         # the graph replays the launches of one eager step: count those
+        n0 = nat.launch_count
+        one_step(eager_mod, *args5)
+        launches_eager = nat.launch_count - n0
     sampler = ClockSampler(local)          # NVML init and thread start-up stay outside the timed region
     sampler.start()
     loss = None
@@ -401,11 +437,11 @@ def run_b200(args):
                    "teacher_tokens": work.n_teacher, "student_dim": work.d_student,
                    "teacher_dim": work.d_teacher, "teacher_layers": work.teacher_layers,
                    "token_dtype": str(work.token_dtype).replace("torch.", ""),
-                   "features": args.features,
+                   "features": args.features, "cuda_graph": bool(args.graph),
                    "cache": "inputs (>=1 GB tokens + attention maps per step) exceed the 126 MB L2",
                    "parallelism": f"dp{world}"},
         "step_ms": [round(x, 2) for x in per_step],
-        "clocks": clocks, "gpu_launches": launches // max(1, args.steps),
+        "clocks": clocks, "gpu_launches": (launches // max(1, args.steps)) or launches_eager,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 4, "ms_per_step": round(float(t.item()), 3),
                 "h2d_gb_per_s_per_gpu": round(h2d / (float(t.item()) * 1e-3) / 1e9, 2),
@@ -418,7 +454,7 @@ def run_b200(args):
     if parity is not None:
         line["dp_parity"] = parity
     # every rank runs the profiled step (the loss all-reduces inside); only rank 0 reports
-    records, total, fp32_peak = roofline(work, mod, args5, pk, clocks)
+    records, total, fp32_peak = roofline(work, eager_mod, args5, pk, clocks)
     if rank == 0:
         line["kernels"] = records[:14]
         line["kernel_ms_total"] = round(total, 3)
@@ -478,6 +514,7 @@ def dp_parity(args, rank, world, device):
 
 # ------------------------------------------------------------------ CPU arms
 def cpu_setup(args, batch):
+    os.sched_setaffinity(0, ORIG_AFFINITY)                # undo the NUMA pinning of the GPU arm: all host cores
     torch.set_num_threads(os.cpu_count())
     work = syn.scaled(syn.WORKLOADS[args.workload], batch)
     mod = build_module(work, "cpu", impl="reference")
@@ -565,6 +602,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dp-parity", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay fwd+bwd from one CUDA graph (graphed.py)")
     ap.add_argument("--features", default="backbone", choices=["backbone", "spectral"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -45,10 +45,16 @@ int basd_sgemm_batched(int trans_a, int trans_b, int M, int N, int K, const void
 /* The pooled covariance behind the MP rank and the layer subspaces (layer_selector.py:13,35,72,88,91) is
  * accumulated in a frame shifted by a rough mean mu0 (covariance is shift invariant), so that the Gram
  * accumulators never hold the M mu mu^T term the centring would have to cancel afterwards (DESIGN.md
- * section 3.1).  mu0[i] = mean of the first rows_sample rows of tensor i (count tensors, one launch).  The
+ * section 3.1).  mu0[i] = mean of rows_sample evenly spaced rows of tensor i (count tensors, one launch).  The
  * Gram entry points below take mu0 (bf16-representable values) and return the statistics of x - mu0. */
 int basd_rough_means(const void* const* tensors, int count, int dtype, long rows, int D, long rows_sample,
                      float* mu0, void* stream);
+/* Data-parallel merge of statistics the ranks accumulated in their OWN frames mu0_r: gram (tensors, D, D) holds
+ * sum_r G'_r on entry (after the all-reduce), d_slots / mu_slots (world, tensors, D) every rank's column sums
+ * and shift; on exit gram, colsum and mu0 (tensors, D) are the statistics of the common frame mean_r mu0_r.
+ * One all-reduce carries everything (the slots of the other ranks are zero in the local buffer). */
+int basd_merge_shifted_stats(float* gram, float* colsum, float* mu0, const float* d_slots, const float* mu_slots,
+                             int world, int tensors, int D, long rows_per_rank, void* stream);
 
 /* Token-space second-moment statistics of one (rows x D) token matrix:
  * gram = X^T X (D x D, symmetric), colsum = X^T 1 (D).  Deterministic split-K.

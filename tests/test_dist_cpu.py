@@ -42,31 +42,38 @@ def _worker(rank, world, port, local_batch, out):
         work = cs.workload("c1", local_batch)
         _, _, st, te, _ = syn.make_inputs(work, seed=4, batch_offset=rank * local_batch)
         layers = sorted(st)
-        # the ranks first agree on the shift (mean of their rough means), then shift, then add statistics:
-        # the contract of _engine.statistics (center.cu)
+        # the contract of _engine.statistics: every rank accumulates in its OWN frame (the rough mean of its
+        # shard, bf16-rounded), ONE all-reduce sums the Grams and carries each rank's column sums and shift in a
+        # slot of its own, then the statistics move to the common frame (center.cu: merge_shifted_stats_kernel)
         tensors = [st[l] for l in layers] + [te[k] for k in sorted(te)]
-        mu0 = torch.cat([t.reshape(-1, t.shape[-1])[:256].mean(0) for t in tensors])
-        _engine._all_reduce(mu0, None)
-        mu0 = mu0 / world
-        shifts, o = [], 0
-        for t in tensors:
-            shifts.append(mu0[o:o + t.shape[-1]])
-            o += t.shape[-1]
+        shifts = [t.reshape(-1, t.shape[-1])[:256].mean(0).bfloat16().float() for t in tensors]
         shifted = [t - m for t, m in zip(tensors, shifts)]
         flat, sizes = _pack([km.token_stats(x) for x in shifted[:len(layers)]],
                             [km.token_stats(x) for x in shifted[len(layers):]])
-        _engine._all_reduce(flat, None)                       # the product's collective helper
+        cols = torch.cat([km.token_stats(x)[1] for x in shifted])
+        mus = torch.cat(shifts)
+        slots = torch.zeros(2, world, cols.numel())
+        slots[0, rank], slots[1, rank] = cols, mus
+        buf = torch.cat([flat, slots.flatten()])
+        _engine._all_reduce(buf, None)                        # the product's collective helper: ONE exchange
+        flat, slots = buf[:flat.numel()], buf[flat.numel():].view(2, world, -1)
         stats_s, stats_t = _unpack(flat, sizes, len(layers), len(te), work.d_student, work.d_teacher)
-        rows = world * local_batch * work.n_student
-
-        def unshift(stat, m):                                 # back to the unshifted frame the CPU model takes
-            g, c = stat[0].double(), stat[1].double()
-            m = m.double()
-            return ((g + torch.outer(m, c) + torch.outer(c, m) + rows * torch.outer(m, m)).float(),
-                    (c + rows * m).float())
-
-        stats_s = [unshift(x, m) for x, m in zip(stats_s, shifts[:len(layers)])]
-        stats_t = [unshift(x, m) for x, m in zip(stats_t, shifts[len(layers):])]
+        rows_local = local_batch * work.n_student
+        rows = world * rows_local
+        merged, o = [], 0
+        for g, _ in stats_s + stats_t:
+            d = g.shape[0]
+            d_r, mu_r = slots[0, :, o:o + d].double(), slots[1, :, o:o + d].double()
+            o += d
+            mu = mu_r.mean(0)
+            delta = mu_r - mu
+            g = g.double() + sum(torch.outer(d_r[r], delta[r]) + torch.outer(delta[r], d_r[r])
+                                 + rows_local * torch.outer(delta[r], delta[r]) for r in range(world))
+            c = (d_r + rows_local * delta).sum(0)
+            # back to the unshifted frame the CPU model takes
+            merged.append(((g + torch.outer(mu, c) + torch.outer(c, mu) + rows * torch.outer(mu, mu)).float(),
+                           (c + rows * mu).float()))
+        stats_s, stats_t = merged[:len(layers)], merged[len(layers):]
         proj_s, proj_t, logt = cs.selector_state(work)
         sel = km.selector_model(stats_s, stats_t, rows, rows, proj_s, proj_t, logt)
         if rank == 0:

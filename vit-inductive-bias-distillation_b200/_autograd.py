@@ -127,9 +127,7 @@ class MixingWeights(torch.autograd.Function):
         step.teachers = [t.detach().contiguous() for t in step.teachers]
         _check_inputs(students, step)
         logt = log_temps.detach().to(torch.float32).contiguous()
-        stats, flat = eng.statistics(students, step.teachers, step.attns, step.has_cls, step.group, step.world)
-        if step.world > 1:
-            eng._all_reduce(flat, step.group)
+        stats, _ = eng.statistics(students, step.teachers, step.attns, step.has_cls, step.group, step.world)
         b, n_s, _ = students[0].shape
         n_t = step.teachers[0].shape[1]
         step.stats = stats

@@ -316,7 +316,7 @@ def importance_rows(attns, b: int, has_cls: bool, dev) -> torch.Tensor:
     return rows
 
 
-ROUGH_MEAN_ROWS = 4096        # token rows behind the rough mean the statistics are shifted by
+ROUGH_MEAN_ROWS = 1024        # evenly spaced token rows behind the rough mean the statistics are shifted by
 
 
 def _ptr_array(tensors):
@@ -327,15 +327,19 @@ def statistics(students, teachers, attns, has_cls, group=None, world: int = 1):
     """Token-space Grams and column sums of every student / teacher tensor, in a MEAN-SHIFTED frame
     (the Gram kernels subtract a rough mean inside the accumulation so that the accumulators never
     hold the M mu mu^T term the centring would otherwise have to cancel), plus the importance rows.
-    Returns (Stats, flat) where `flat` is the one buffer data-parallel ranks all-reduce; the ranks agree on
-    the shift first (an all-reduce of E D_s + L D_t floats) so that their statistics add."""
+
+    Data parallel (world > 1): every rank accumulates in its OWN frame (the rough mean of its shard) and
+    ONE all-reduce of a flat buffer sums the Grams and carries each rank's column sums and shift in a slot
+    of its own; `basd_merge_shifted_stats` then moves everything to the common frame.  Returns
+    (Stats of the global batch, the flat buffer that was exchanged)."""
     dev = students[0].device
     e, l = len(students), len(teachers)
     b, n_t, d_t = teachers[0].shape
     n_s, d_s = students[0].shape[1], students[0].shape[2]
-    # one flat buffer so the data-parallel exchange is a single all-reduce
+    slot = e * d_s + l * d_t
     sizes = [e * d_s * d_s, e * d_s, l * d_t * d_t, l * d_t]
-    flat = _f32(sum(sizes), device=dev)
+    extra = 2 * world * slot if world > 1 else 0
+    flat = _f32(sum(sizes) + extra, device=dev)
     offs = [0]
     for s in sizes:
         offs.append(offs[-1] + s)
@@ -343,14 +347,11 @@ def statistics(students, teachers, attns, has_cls, group=None, world: int = 1):
     col_s = flat[offs[1]:offs[2]].view(e, d_s)
     gram_t = flat[offs[2]:offs[3]].view(l, d_t, d_t)
     col_t = flat[offs[3]:offs[4]].view(l, d_t)
-    mu0 = _f32(e * d_s + l * d_t, device=dev)
+    mu0 = _f32(slot, device=dev)
     mu0_s, mu0_t = mu0[:e * d_s].view(e, d_s), mu0[e * d_s:].view(l, d_t)
     for tensors, nrows, d, m0 in ((students, b * n_s, d_s, mu0_s), (teachers, b * n_t, d_t, mu0_t)):
         call("basd_rough_means", _ptr_array(tensors), len(tensors), nat.dtype_code(tensors[0]), nrows, d,
              min(nrows, ROUGH_MEAN_ROWS), ptr(m0), stream())
-    if world > 1:                                         # the ranks' statistics only add under ONE shift
-        _all_reduce(mu0, group)
-        mu0 /= world
     # the correction operand of the tensor-core Gram holds 8 mu0 in bf16: it must be exact
     mu0 = mu0.to(torch.bfloat16).to(torch.float32)
     mu0_s, mu0_t = mu0[:e * d_s].view(e, d_s), mu0[e * d_s:].view(l, d_t)
@@ -358,6 +359,28 @@ def statistics(students, teachers, attns, has_cls, group=None, world: int = 1):
         token_gram(s, gram_s[i], col_s[i], mu0_s[i])
     for j, t in enumerate(teachers):
         token_gram(t, gram_t[j], col_t[j], mu0_t[j])
+    if world > 1:
+        # slots (world, E, D_s) / (world, L, D_t) for the column sums and for the shifts: this rank fills its
+        # own, the all-reduce (sum) delivers everybody's
+        rank = dist.get_rank(group)
+        tail = flat[offs[4]:]
+        tail.zero_()
+        d_s_slots = tail[:world * e * d_s].view(world, e, d_s)
+        m_s_slots = tail[world * e * d_s:2 * world * e * d_s].view(world, e, d_s)
+        rest = tail[2 * world * e * d_s:]
+        d_t_slots = rest[:world * l * d_t].view(world, l, d_t)
+        m_t_slots = rest[world * l * d_t:].view(world, l, d_t)
+        d_s_slots[rank].copy_(col_s)
+        m_s_slots[rank].copy_(mu0_s)
+        d_t_slots[rank].copy_(col_t)
+        m_t_slots[rank].copy_(mu0_t)
+        _all_reduce(flat, group)
+        mu0 = _f32(slot, device=dev)
+        mu0_s, mu0_t = mu0[:e * d_s].view(e, d_s), mu0[e * d_s:].view(l, d_t)
+        call("basd_merge_shifted_stats", ptr(gram_s), ptr(col_s), ptr(mu0_s), ptr(d_s_slots), ptr(m_s_slots), world,
+             e, d_s, b * n_s, stream())
+        call("basd_merge_shifted_stats", ptr(gram_t), ptr(col_t), ptr(mu0_t), ptr(d_t_slots), ptr(m_t_slots), world,
+             l, d_t, b * n_t, stream())
     rows = importance_rows(attns, b, has_cls, dev)
     return Stats(gram_s, col_s, gram_t, col_t, rows, mu0_s, mu0_t), flat
 

@@ -23,6 +23,7 @@ _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_long, C.c_float
 _SIG = {
     "basd_sgemm_batched": [_i, _i, _i, _i, _i, _p, _i, _i, _l, _p, _p, _i, _l, _p, _i, _l, _i, _f, _p, _f, _p],
     "basd_rough_means": [_p, _i, _i, _l, _i, _l, _p, _p],
+    "basd_merge_shifted_stats": [_p, _p, _p, _p, _p, _i, _i, _i, _l, _p],
     "basd_token_gram_simt_workspace_floats": [_l, _i],
     "basd_token_gram_simt": [_p, _i, _l, _i, _p, _p, _p, _p, _p],
     "basd_pivoted_cholesky": [_p, _i, _i, _l, _p, _i, _l, _i, _f, _p, _p, _p],

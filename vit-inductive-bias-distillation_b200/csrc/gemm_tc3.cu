@@ -14,11 +14,13 @@
 //                (bank-conflict-free: 16 k x 2 column quads per warp), so one descriptor type
 //                serves all four op() combinations.
 //   warp 8     : one thread issues tcgen05.mma (M = 128, N = BN, K = 8), tcgen05.commit frees the
-//                stage; 2-3 stage mbarrier ring.
-//   warps 0..3 : epilogue, tcgen05.ld 32x32b -> registers -> alpha -> global.
+//                stage (one stage per CTA, two CTAs per SM).
+//   warps 0..7 : epilogue, tcgen05.ld 32x32b -> registers -> alpha -> global (warps w and w + 4 share a
+//                TMEM lane quarter and split its columns).
 // Replaces the SIMT batched SGEMM (gemm_simt.cu) for the Procrustes products
 // (reference: torch.bmm at relational.py:47 and the matmuls inside linalg.svd's backward).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace basd {
 namespace tc3 {
@@ -106,9 +108,8 @@ __device__ __forceinline__ uint32_t sw_off(int row, int k) {
                                ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
 }
 
-// The producers keep TWO register sets of raw tiles: the global loads of slab kb+1 are in flight
-// while slab kb is split and written to shared memory (a slab is only ~43 KB, so without this the
-// K loop runs at one global-memory latency per slab).
+// The global loads of slab kb+1 are issued right after slab kb has been split and written to shared memory,
+// so they are in flight while the tensor core works on slab kb; the second CTA of the SM covers the rest.
 //
 // Operand whose contraction index is contiguous in memory (row-major R x K with pitch ld):
 // one float4 = 4 consecutive k of one row; a quarter warp covers one 128-byte row -> conflict-free
@@ -238,7 +239,13 @@ struct Params {
   int c_bf16;              // store C as bf16
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+// One shared-memory stage and one register set of raw tiles per CTA, compiled for TWO CTAs per SM (96
+// registers, <= 97 KB of shared memory, 256 TMEM columns each).  A tile of these batched products is short
+// (K = 196: seven slabs, then an epilogue nothing overlaps), so one pipelined CTA per SM (round 1: two or
+// three stages, two register sets, 168 registers) left the SM idle through every prologue, load latency and
+// epilogue: ncu showed tensor pipe 20 %, DRAM 14 %, issue slots 33 % -- nothing saturated.  Two resident
+// CTAs fill each other's gaps: 5.97 -> 5.01 ms for the 30 launches of a C2 step, measured on B200.
+__global__ void __launch_bounds__(THREADS, 2)
 gemm_tc3_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -279,7 +286,7 @@ gemm_tc3_kernel(const Params p) {
   if (warp < PRODUCER_WARPS) {
     // ===== producers =====
     const int ptid = threadIdx.x;
-    float4 va[2][A_ITEMS], vb[2][B_ITEMS];
+    float4 va[1][A_ITEMS], vb[1][B_ITEMS];
     auto issue = [&](int set, int kb) {
       const int k0 = kb * KS;
       if (p.a_bf16) issue_kcontig_bf16(va[set], reinterpret_cast<const __nv_bfloat16*>(p.A) + prob * p.sa,
@@ -307,11 +314,9 @@ gemm_tc3_kernel(const Params p) {
       if (lane == 0) mbar_arrive(&full_bar[s]);
     };
     if (num_kb > 0) issue(0, 0);
-    for (int kb = 0; kb < num_kb; kb += 2) {
-      if (kb + 1 < num_kb) issue(1, kb + 1);
+    for (int kb = 0; kb < num_kb; ++kb) {
       publish(0, kb);
-      if (kb + 2 < num_kb) issue(0, kb + 2);
-      if (kb + 1 < num_kb) publish(1, kb + 1);
+      if (kb + 1 < num_kb) issue(0, kb + 1);             // in flight while the MMAs of slab kb run
     }
   } else if (lane == 0) {
     // ===== MMA issuer (one thread) =====
@@ -343,17 +348,55 @@ gemm_tc3_kernel(const Params p) {
     umma_commit(tmem_full_bar);
   }
 
-  if (warp < 4) {
+  if (warp < PRODUCER_WARPS) {
     // ===== epilogue: TMEM -> registers -> global =====
+    // All eight producer warps take part: warp w may read TMEM lanes 32 (w % 4) .. + 31, so warps w and
+    // w + 4 share a row quarter and split its columns.  Two 16-column loads are in flight per wait.
+    // (Four warps walking all BN columns one load at a time made the epilogue ~8 of the ~28 us a
+    // 128 x 256 x 196 tile takes: the tile is short, nothing overlaps the epilogue.)
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float alpha = p.alpha_dev ? p.alpha * p.alpha_dev[0] : p.alpha;
-    const int row = m0 + warp * 32 + lane;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = m0 + quarter * 32 + lane;
     const int ncols = min(p.BN, p.N - n0);
-#pragma unroll 1
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
-      uint32_t v[16];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0;
+    const int split = min(ncols, ((ncols + 31) / 32) * 16);          // multiple of 16
+    const int c_begin = half ? split : 0, c_end = half ? ncols : split;
+    auto store16 = [&](const uint32_t (&v)[16], int c0) {
+      if (row >= p.M) return;
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = __uint_as_float(v[i]);
+        if (p.col_sub && c0 + i < ncols) a -= p.col_sub[n0 + c0 + i];
+        o[i] = alpha * a;
+      }
+      if (p.c_bf16) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + prob * p.sc +
+                             static_cast<long>(row) * p.ldc + n0 + c0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (c0 + 4 * i < ncols) {
+            const __nv_bfloat162 lo2 = __floats2bfloat162_rn(o[4 * i], o[4 * i + 1]);
+            const __nv_bfloat162 hi2 = __floats2bfloat162_rn(o[4 * i + 2], o[4 * i + 3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo2);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
+            *reinterpret_cast<uint2*>(dst + 4 * i) = pk;
+          }
+        }
+      } else {
+        float* dst = C + static_cast<long>(row) * p.ldc + n0 + c0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (c0 + 4 * i < ncols)
+            *reinterpret_cast<float4*>(dst + 4 * i) =
+                make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+      }
+    };
+    auto load16 = [&](uint32_t (&v)[16], int c0) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -361,39 +404,16 @@ gemm_tc3_kernel(const Params p) {
             "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
             "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
           : "r"(taddr));
+    };
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      uint32_t v0[16], v1[16];
+      const bool two = c0 + 16 < c_end;                  // warp-uniform
+      load16(v0, c0);
+      if (two) load16(v1, c0 + 16);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < p.M) {
-        float o[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a = __uint_as_float(v[i]);
-          if (p.col_sub && c0 + i < ncols) a -= p.col_sub[n0 + c0 + i];
-          o[i] = alpha * a;
-        }
-        if (p.c_bf16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + prob * p.sc +
-                               static_cast<long>(row) * p.ldc + n0 + c0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (c0 + 4 * i < ncols) {
-              const __nv_bfloat162 lo2 = __floats2bfloat162_rn(o[4 * i], o[4 * i + 1]);
-              const __nv_bfloat162 hi2 = __floats2bfloat162_rn(o[4 * i + 2], o[4 * i + 3]);
-              uint2 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&lo2);
-              pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
-              *reinterpret_cast<uint2*>(dst + 4 * i) = pk;
-            }
-          }
-        } else {
-          float* dst = C + static_cast<long>(row) * p.ldc + n0 + c0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (c0 + 4 * i < ncols)
-              *reinterpret_cast<float4*>(dst + 4 * i) =
-                  make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-          }
-        }
-      }
+      store16(v0, c0);
+      if (two) store16(v1, c0 + 16);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -451,13 +471,11 @@ extern "C" int basd_gemm_tc3_batched_ex(int ta, int tb, int M, int N, int K, con
   p.BN = bn;
   p.tiles_n = (N + bn - 1) / bn;
   const int stage_bytes = 2 * A_BYTES + 2 * bn * 128;
-  int stages = (SMEM_LIMIT - 2048) / stage_bytes;
-  if (stages > 4) stages = 4;
-  if (stages < 2) return -5;
-  p.stages = stages;
+  p.stages = 1;
   p.alpha = alpha;
   p.alpha_dev = alpha_dev;
-  const int dyn = stages * stage_bytes + 1024 + 256;
+  const int dyn = stage_bytes + 1024 + 256;
+  if (2 * dyn > SMEM_LIMIT) return -5;
   BASD_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   dim3 grid(((M + TM - 1) / TM) * p.tiles_n, batch);
   gemm_tc3_kernel<<<grid, THREADS, dyn, (cudaStream_t)stream>>>(p);
