@@ -94,7 +94,7 @@ def measured_traffic():
     byte model, from the committed `ncu --set full` captures (profiles/r2_traffic.json)."""
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(path):
-        return json.load(open(path))
+        return json.load(open(path)).get("per_launch_dram_bytes", {})
     return {}
 
 
