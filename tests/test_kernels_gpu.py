@@ -378,3 +378,30 @@ def test_rotate_stats_f64_rounds_once(d_out, d_in, batch):
     assert ((k.double() - ref).abs() <= 6.1e-8 * ref.abs() + 1e-11 * scale).all()
     assert (k - k.transpose(1, 2)).abs().max() == 0
     assert ((chat.double() - c64).abs() <= 6.1e-8 * c64.abs() + 1e-11 * c64.abs().max()).all()
+
+
+def test_merge_shifted_stats_matches_the_common_frame():
+    """Statistics accumulated by W ranks in their own mean-shifted frames, merged by
+    basd_merge_shifted_stats, equal the statistics of the concatenated rows in the common frame
+    mean_r mu0_r (center.cu; the data-parallel contract of _engine.statistics)."""
+    from basd_b200._native import call, ptr, stream
+    torch.manual_seed(11)
+    world, tensors, d, rows = 3, 2, 96, 500
+    x = (torch.randn(world, tensors, rows, d, device=DEV, dtype=torch.float64) * torch.logspace(0, -1, d, device=DEV)
+         + 5.0 * torch.randn(tensors, 1, d, device=DEV, dtype=torch.float64))
+    mu_r = (x[:, :, :64].mean(2) + 0.05 * torch.randn(world, tensors, d, device=DEV)).float()      # rough, per rank
+    xs = x - mu_r.double().unsqueeze(2)
+    gram = torch.einsum("wtnd,wtne->tde", xs, xs).float().contiguous()        # what the all-reduce sums
+    d_slots = xs.sum(2).float().contiguous()
+    col = torch.empty(tensors, d, device=DEV)
+    mu0 = torch.empty(tensors, d, device=DEV)
+    call("basd_merge_shifted_stats", ptr(gram), ptr(col), ptr(mu0), ptr(d_slots), ptr(mu_r.contiguous()), world,
+         tensors, d, rows, stream())
+    mu = mu_r.double().mean(0)
+    xc = x - mu.unsqueeze(0).unsqueeze(2)
+    ref_g = torch.einsum("wtnd,wtne->tde", xc, xc)
+    ref_c = xc.sum((0, 2))
+    assert (mu0.double() - mu).abs().max() < 1e-6
+    assert (gram.double() - ref_g).abs().max() / ref_g.abs().max() < 1e-5
+    assert (col.double() - ref_c).abs().max() < 1e-3 * max(1.0, float(ref_c.abs().max()))
+    assert (gram - gram.transpose(1, 2)).abs().max() == 0
