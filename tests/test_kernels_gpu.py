@@ -401,7 +401,7 @@ def test_merge_shifted_stats_matches_the_common_frame():
     xc = x - mu.unsqueeze(0).unsqueeze(2)
     ref_g = torch.einsum("wtnd,wtne->tde", xc, xc)
     ref_c = xc.sum((0, 2))
-    assert (mu0.double() - mu).abs().max() < 1e-6
+    assert (mu0.double() - mu).abs().max() < 1e-5          # fp32 mean of values ~10
     assert (gram.double() - ref_g).abs().max() / ref_g.abs().max() < 1e-5
     assert (col.double() - ref_c).abs().max() < 1e-3 * max(1.0, float(ref_c.abs().max()))
     assert (gram - gram.transpose(1, 2)).abs().max() == 0

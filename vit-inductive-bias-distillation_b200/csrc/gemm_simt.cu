@@ -583,11 +583,21 @@ extern "C" int basd_sgemm_batched(int trans_a, int trans_b, int M, int N, int K,
                                   stride_b, C, ldc, stride_c, batch, alpha, alpha_dev, beta, st);
 }
 
-extern "C" long basd_token_gram_simt_workspace_floats(long rows, int D) {
+// Split-K slices of the SIMT Gram: 2,048 rows each for large inputs, but never so few that the grid
+// (upper tiles x slices) leaves most of the GPU idle -- C1 (1,024 rows, D = 192) ran 6 CTAs per launch.
+static long simt_gram_slices(long rows, int D) {
+  const long tiles = (D + basd::BM - 1) / basd::BM, upper = tiles * (tiles + 1) / 2;
   long slices = (rows + 2047) / 2048;
+  const long want = (2 * 148 + upper - 1) / upper;            // about two waves of CTAs
+  const long by_rows = (rows + 127) / 128;                    // at least 128 rows per slice
+  if (slices < want) slices = want < by_rows ? want : by_rows;
   if (slices > 64) slices = 64;
   if (slices < 1) slices = 1;
-  return slices * ((long)D * D + D);
+  return slices;
+}
+
+extern "C" long basd_token_gram_simt_workspace_floats(long rows, int D) {
+  return simt_gram_slices(rows, D) * ((long)D * D + D);
 }
 
 // gram[D*D] = X'^T X', colsum[D] = X'^T 1 for X' = tokens - 1 mu0^T viewed as (rows, D); mu0 (D floats,
@@ -597,9 +607,7 @@ extern "C" int basd_token_gram_simt(const void* tokens, int dtype, long rows, in
                                     float* gram, float* colsum, float* workspace, void* stream) {
   using namespace basd;
   cudaStream_t st = (cudaStream_t)stream;
-  long slices = (rows + 2047) / 2048;
-  if (slices > 64) slices = 64;
-  if (slices < 1) slices = 1;
+  const long slices = simt_gram_slices(rows, D);
   long per = (rows + slices - 1) / slices;
   per = (per + BK - 1) / BK * BK;
   const int tiles = (D + BM - 1) / BM;
