@@ -139,7 +139,7 @@ def test_token_gram_in_a_mean_shifted_frame(dtype, rows, d):
     raw_scale = float((x.double().T @ x.double()).abs().max())
     print(f"rows {rows} d {d} {dtype}: max err / cov scale {err / scale:.2e} (uncentred scale is {raw_scale / scale:.0f}x)")
     assert err / scale < 2e-5
-    assert (col.double() - xs.sum(0)).abs().max() < 1e-4 * max(1.0, float(xs.sum(0).abs().max()))
+    assert (col.double() - xs.sum(0)).abs().max() < 1e-3 * max(1.0, float(xs.sum(0).abs().max()))
     assert (gram - gram.T).abs().max() == 0
 
 

@@ -83,6 +83,8 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float out[8]) {
 int launch_gram_reduce(const float* partial, int slices, int D, int tile, float* gram,
                        cudaStream_t st, const float* mu0 = nullptr, const float* dsum = nullptr,
                        float coef = 0.f);
+int launch_colsum_fold(const float* partial, int slices, int D, float* out, const float* mu0, float coef,
+                       cudaStream_t st);
 int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial /* >= 64*D floats */,
                        float* out, cudaStream_t st, const float* mu0 = nullptr);
 

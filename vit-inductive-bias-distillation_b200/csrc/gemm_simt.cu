@@ -533,6 +533,24 @@ int launch_gram_reduce(const float* partial, int slices, int D, int tile, float*
   return 0;
 }
 
+// out[d] = sum_slices partial[s][d] + coef * mu0[d]   (column sums that rode on the tensor-core Gram: its
+// accumulator holds sum x - Mc mu0, the shifted column sum is sum x - M mu0, coef = Mc - M)
+__global__ void colsum_fold_kernel(const float* __restrict__ partial, int slices, int D, float* __restrict__ out,
+                                   const float* __restrict__ mu0, float coef) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int i = 0; i < slices; ++i) s += partial[(long)i * D + d];
+  out[d] = mu0 ? fmaf(coef, mu0[d], s) : s;
+}
+
+int launch_colsum_fold(const float* partial, int slices, int D, float* out, const float* mu0, float coef,
+                       cudaStream_t st) {
+  colsum_fold_kernel<<<(D + 127) / 128, 128, 0, st>>>(partial, slices, D, out, mu0, coef);
+  BASD_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial, float* out,
                        cudaStream_t st, const float* mu0) {
   int cs = (int)((rows + 4095) / 4096);

@@ -34,15 +34,25 @@ namespace tc {
 
 constexpr int TILE = 128;                 // UMMA M = N = 128
 constexpr int BK = 64;                    // token rows per stage
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int BOX_BYTES = BK * 128;       // one TMA box: 64 bf16 columns x BK rows
 constexpr int OPERAND_BYTES = 2 * BOX_BYTES;
-constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;
+// a stage = A (two boxes) | B (two boxes) | a constant box of ones that extends B to N = 144 (column sums)
+constexpr int STAGE_BYTES = 2 * OPERAND_BYTES + BOX_BYTES;
 constexpr int MU_ROWS = 16;               // one UMMA K step: row 0 = 8 mu0, rows 1..15 = 0
 constexpr int MU_BOX_BYTES = MU_ROWS * 128;
 constexpr int MU_BYTES = 4 * MU_BOX_BYTES;        // A (two 64-column boxes) + B (two boxes)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + MU_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 128;
+// Column sums on the tensor core: X^T 1 is one more GEMM column.  On diagonal tiles the B operand is
+// N = 144 wide: its third 64-column chunk is a constant box of ones kept behind the B boxes of every stage
+// (16 of its columns are used), so the SAME UMMA that forms the Gram tile also accumulates the column sums in
+// TMEM columns 128..143 -- the A tile is read once (a separate N = 16 UMMA re-read it and cost as much
+// shared-memory bandwidth as the column-sum pass it replaced: 45.8 -> 65.7 us per D = 768 layer).  The
+// mean-shift correction operand is extended the same way by a chunk whose first row is 8 (negated:
+// -(8 mu0) 8 = -64 mu0 per stage).  The token stack is read once.
+constexpr int ONES_BYTES = MU_BOX_BYTES;          // "8 in row 0" chunk of the correction operand
+constexpr int CS_N = 16;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + MU_BYTES + ONES_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 256;            // 128 (Gram tile) + 16 (column sums), power of two
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -114,6 +124,9 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u
                            ((TILE >> 3) << 17) | ((TILE >> 4) << 24);
 
 constexpr uint32_t IDESC_NEG_B = IDESC | (1u << 14);      // bit 14: negate B
+constexpr uint32_t IDESC_CS = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                              (((TILE + CS_N) >> 3) << 17) | ((TILE >> 4) << 24);      // N = 144
+constexpr uint32_t IDESC_CS_NEG_B = IDESC_CS | (1u << 14);
 
 // mu tile (16 x D bf16, row-major): row 0 = 8 mu0, rows 1..15 = 0
 __global__ void mu_tile_kernel(const float* __restrict__ mu0, int D, __nv_bfloat16* __restrict__ tile) {
@@ -124,12 +137,14 @@ __global__ void mu_tile_kernel(const float* __restrict__ mu0, int D, __nv_bfloat
 
 __global__ void __launch_bounds__(192, 1)
 token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_mu,
-                     int use_mu, float* __restrict__ partial, int D, long rows, long rows_per_slice) {
+                     int use_mu, float* __restrict__ partial, float* __restrict__ partial_cs /* (slices, D) or null */,
+                     int D, long rows, long rows_per_slice) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* mu_smem = smem + STAGES * STAGE_BYTES;         // 1024-byte aligned (swizzle atom)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(mu_smem + MU_BYTES);
+  uint8_t* ones_smem = mu_smem + MU_BYTES;                // third chunk of the correction B operand: row 0 = 8
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones_smem + ONES_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* mu_bar = tmem_full_bar + 1;
@@ -143,6 +158,16 @@ token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   const long k_begin = static_cast<long>(blockIdx.y) * rows_per_slice;
   const long k_end = min(rows, k_begin + rows_per_slice);
   const int num_kb = k_end > k_begin ? static_cast<int>((k_end - k_begin + BK - 1) / BK) : 0;
+  const bool do_cs = partial_cs != nullptr && ti == tj;   // the diagonal tiles cover every column once
+  if (do_cs) {                                            // constant operands (row 0 is not swizzled: r & 7 = 0)
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ones_smem);
+    for (int i = threadIdx.x; i < MU_ROWS * 64; i += blockDim.x) o[i] = __float2bfloat16(i < 64 ? 8.f : 0.f);
+    for (int st = 0; st < STAGES; ++st) {                 // the ones box behind the B boxes of every stage
+      uint32_t* w = reinterpret_cast<uint32_t*>(smem + st * STAGE_BYTES + 2 * OPERAND_BYTES);
+      for (int i = threadIdx.x; i < BOX_BYTES / 4; i += blockDim.x) w[i] = 0x3f803f80u;   // two bf16 ones
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> UMMA reads
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -176,7 +201,7 @@ token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        mbar_expect_tx(&full_bar[s], 2 * OPERAND_BYTES);
         uint8_t* a = smem + s * STAGE_BYTES;
         uint8_t* b = a + OPERAND_BYTES;
         const int k0 = static_cast<int>(k_begin + static_cast<long>(kb) * BK);
@@ -203,12 +228,12 @@ token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         const uint32_t a = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t b = a + OPERAND_BYTES;
         // -(8 mu0)(8 mu0)^T = -BK mu0 mu0^T first: the accumulator never holds more than one stage of it
-        if (use_mu) umma_bf16(tmem_base, dmu_a, dmu_b, IDESC_NEG_B, kb > 0 ? 1u : 0u);
+        if (use_mu) umma_bf16(tmem_base, dmu_a, dmu_b, do_cs ? IDESC_CS_NEG_B : IDESC_NEG_B, kb > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {           // UMMA K = 16 rows = 2 x (8 rows x 128 B)
           const uint64_t da = make_desc(a + k * 2048);
           const uint64_t db = make_desc(b + k * 2048);
-          umma_bf16(tmem_base, da, db, IDESC, (use_mu || kb > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, da, db, do_cs ? IDESC_CS : IDESC, (use_mu || kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);                   // frees the smem slot when the MMAs retire
       }
@@ -221,6 +246,15 @@ token_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     if (num_kb > 0) {
       mbar_wait(tmem_full_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (do_cs) {                                      // column 0 of the 16 ones-columns: sum over this slice's rows
+      uint32_t c = 0u;
+      if (num_kb > 0) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + TILE;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(c) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
+      partial_cs[static_cast<long>(blockIdx.y) * D + row] = __uint_as_float(c);
     }
 #pragma unroll 1
     for (int c0 = 0; c0 < TILE; c0 += 16) {
@@ -338,20 +372,25 @@ extern "C" int basd_token_gram_tc(const void* tokens, long rows, int D, const fl
       const long k_begin = static_cast<long>(s) * per, k_end = rows < k_begin + per ? rows : k_begin + per;
       if (k_end > k_begin) corrected += (k_end - k_begin + BK - 1) / BK * BK;
     }
-    // column sums of the shifted tokens first: the reduce below needs them
-    if (int e = launch_colsum_bf16(tokens, rows, D, part_c, colsum, st, mu0)) return e;
   } else {
     tmap_mu = tmap;
   }
+  // column sums ride on the tensor core (diagonal tiles); with a shift the kernel's accumulator is
+  // sum x - Mc mu0: the slices' partials are folded by the column-sum reduce kernel, then d = sum (x - mu0)
+  // needs + (Mc - M) mu0, applied by the Gram reduce below together with its own conversion
+  const bool fused_cs = colsum != nullptr && slices <= 64;
   BASD_CUDA(cudaFuncSetAttribute(token_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SMEM_BYTES));
   dim3 grid(tiles * (tiles + 1) / 2, slices);
-  token_gram_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tmap, tmap_mu, mu0 ? 1 : 0, part_g, D, rows, per);
+  token_gram_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tmap, tmap_mu, mu0 ? 1 : 0, part_g, fused_cs ? part_c : nullptr, D,
+                                                      rows, per);
   BASD_LAUNCH_CHECK();
-  if (int e = launch_gram_reduce(part_g, slices, D, TILE, gram, st, mu0, colsum,
-                                 static_cast<float>(corrected - rows)))
-    return e;
-  if (mu0 || !colsum) return 0;
-  // column sums (HBM-bound, one extra pass over the tokens)
-  return launch_colsum_bf16(tokens, rows, D, part_c, colsum, st);
+  if (colsum) {
+    if (fused_cs) {
+      if (int e = launch_colsum_fold(part_c, slices, D, colsum, mu0, static_cast<float>(corrected - rows), st)) return e;
+    } else if (int e = launch_colsum_bf16(tokens, rows, D, part_c, colsum, st, mu0)) {
+      return e;
+    }
+  }
+  return launch_gram_reduce(part_g, slices, D, TILE, gram, st, mu0, colsum, static_cast<float>(corrected - rows));
 }
