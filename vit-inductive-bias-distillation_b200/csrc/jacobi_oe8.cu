@@ -574,15 +574,19 @@ jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, lo
       apply<NF>(x0, r[0], 1 < cnt, T1[0], T2[0]);
 #pragma unroll
       for (int j = 0; j < NF; ++j) my_row[G * j] = x0[j];
+      // Split-phase cluster barrier: everything other groups read (position 0 and its state) is written,
+      // so ARRIVE now and run the register-only work -- the three remaining rotations and the three local
+      // dot products of the odd step -- under the barrier's ~380-cycle latency before WAITING.
+      cluster.barrier_arrive();
 #pragma unroll
       for (int k = 1; k < 4; ++k) apply<NF>(r[2 * k - 1], r[2 * k], 2 * k + 1 < cnt, T1[k], T2[k]);
-      cluster.sync();
       // ---------------- odd step: the neighbour's position 0 (possibly remote) into registers first
       if (step + 1 < nn) {
 #pragma unroll
-        for (int j = 0; j < NF; ++j) x0[j] = right_row[G * j];
-#pragma unroll
         for (int k = 0; k < 3; ++k) ga[k] = dot_local<NF>(r[2 * k], r[2 * k + 1]);
+        cluster.barrier_wait();
+#pragma unroll
+        for (int j = 0; j < NF; ++j) x0[j] = right_row[G * j];
         ga[3] = dot_local<NF>(r[R - 2], x0);
         angle_pass_ptr<G, 1>(reduce4_owner<G>(ga, gl), sn, sd, xs_my, xs_right, gl, cnt, cross_ok, tol2, zero_thr,
                           worst, nrot, T1, T2);
@@ -591,10 +595,11 @@ jacobi_rows_oe8_cluster_body(float* __restrict__ Gbase, int n, int m, int ld, lo
 #pragma unroll
           for (int j = 0; j < NF; ++j) right_row[G * j] = x0[j];
         }
+        cluster.barrier_arrive();
 #pragma unroll
         for (int k = 0; k < 3; ++k) apply<NF>(r[2 * k], r[2 * k + 1], 2 * k + 2 < cnt, T1[k], T2[k]);
       }
-      cluster.sync();
+      cluster.barrier_wait();
     }
     const float all_worst = wide_max(worst, 1);
     cluster.sync();                                      // everyone has read the flags before rank 0 resets them

@@ -8,7 +8,8 @@
 // 2e3 the fp32 rotation alone takes the student-gradient cosine against the reference from 0.99999
 // to 0.9989 (CPU model, oracle/kernel_model.py); accumulating G itself in fp64 changes nothing.
 // The work is tiny (8 GFLOP at C2), so plain DFMA tiles are enough: 64 x 64 output tiles, 4 x 4
-// doubles per thread, operands converted to double while they are staged in shared memory.
+// doubles per thread (columns tx + 16 j: conflict-free shared-memory reads), operands converted to double
+// on their way through registers into shared memory, the next slab prefetched during the multiply.
 #include "common.cuh"
 
 namespace basd {
@@ -39,33 +40,48 @@ dgemm_kernel(int M, int N, int K, const TA* __restrict__ A, int lda, long stride
   const int sr = tid >> 2, sk = (tid & 3) * 4;
   // and a 16 x 64 slab read along its 64-wide side
   const int br = tid >> 4, bc = (tid & 15) * 4;
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  // the next slab travels in registers while the current one is multiplied
+  double ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int m = m0 + sr, k = k0 + sk + e;
-      As[sk + e][sr] = (m < M && k < K) ? (double)A[(long)m * lda + k] : 0.0;
+      ra[e] = (m < M && k < K) ? (double)A[(long)m * lda + k] : 0.0;
     }
     if (TRANS_B) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int n = n0 + sr, k = k0 + sk + e;
-        Bs[sk + e][sr] = (n < N && k < K) ? (double)B[(long)n * ldb + k] : 0.0;
+        rb[e] = (n < N && k < K) ? (double)B[(long)n * ldb + k] : 0.0;
       }
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int k = k0 + br, n = n0 + bc + e;
-        Bs[br][bc + e] = (k < K && n < N) ? (double)B[(long)k * ldb + n] : 0.0;
+        rb[e] = (k < K && n < N) ? (double)B[(long)k * ldb + n] : 0.0;
       }
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) As[sk + e][sr] = ra[e];
+    if (TRANS_B) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[sk + e][sr] = rb[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[br][bc + e] = rb[e];
+    }
     __syncthreads();
+    if (k0 + TK < K) fetch(k0 + TK);
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];       // one address per half-warp: broadcast
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];      // consecutive lanes, consecutive doubles
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -79,7 +95,7 @@ dgemm_kernel(int M, int N, int K, const TA* __restrict__ A, int lda, long stride
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+      const int n = n0 + tx + 16 * j;
       if (n < N) C[(long)m * ldc + n] = acc[i][j];
     }
   }
