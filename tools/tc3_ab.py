@@ -37,6 +37,26 @@ def run(batch):
         ref = (a.transpose(1, 2) if ta else a).double() @ (bb.transpose(1, 2) if tb else bb).double()
         err = float((c.double() - ref).abs().max() / ref.abs().max())
         out[(ta, tb, m, n, k)] = (e0.elapsed_time(e1) / 5, c.cpu(), err)
+    # the selector backward product: bf16 tokens (A) x fp32 W, column shift in the epilogue, bf16 output
+    m, n, k = 50176, 384, 384
+    torch.manual_seed(5)
+    a = (torch.randn(m, k, device=dev) + 0.5).bfloat16()
+    w = torch.randn(k, n, device=dev) / k ** 0.5
+    shift = (a.float().mean(0).double() @ w.double()).float()
+    c = torch.full((m, n), float("nan"), device=dev, dtype=torch.bfloat16)
+    args = (0, 0, m, n, k, a, k, 0, w, n, 0, c, n, 0, 1)
+    for _ in range(2):
+        assert eng.gemm_tc_ex(*args, alpha=2.0, col_sub=shift)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        eng.gemm_tc_ex(*args, alpha=2.0, col_sub=shift)
+    e1.record()
+    torch.cuda.synchronize()
+    ref = 2.0 * ((a.double() - a.double().mean(0)) @ w.double())
+    err = float((c.double() - ref).abs().max() / ref.abs().max())
+    out[("bf16A", 0, m, n, k)] = (e0.elapsed_time(e1) / 5, c.float().cpu(), err)
     return out
 
 

@@ -519,6 +519,7 @@ struct TParams {
   int M, N, K, ldc;
   long sc;
   int ta, tb;                 // 1: operand stored with the contraction index as the slow dimension
+  int a_bf16;                 // A is bf16 (ta = 0): exact in TF32 -- expanded by the split warps, no lo term
   int a_batched, b_batched;   // 0: one operand shared by the whole batch
   int BN, bnp, tiles_m, tiles_n, batch;
   int raw_stages, lo_stages;
@@ -608,7 +609,7 @@ gemm_tc3_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == T_EPI_WARPS + T_CONV_WARPS) {
     if (lane == 0) {
       // ===== TMA producer =====
-      const uint32_t tx = A_BYTES + (p.tb ? p.BN * 128 : b_bytes);
+      const uint32_t tx = (p.a_bf16 ? A_BYTES / 2 : A_BYTES) + (p.tb ? p.BN * 128 : b_bytes);
       long it = 0;
       for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int prob = static_cast<int>(tile / tpp), r = static_cast<int>(tile - static_cast<long>(prob) * tpp);
@@ -621,7 +622,9 @@ gemm_tc3_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(&raw_full[s], tx);
           const uint32_t a = raw0 + s * slab_bytes, b = a + A_BYTES;
           const int k0 = kb * KS;
-          if (p.ta) {
+          if (p.a_bf16) {                               // dense 128 x 32 bf16 rows in the upper half of the A slab
+            tma_load_3d(a + A_BYTES / 2, &tmA, &raw_full[s], k0, m0, pa);
+          } else if (p.ta) {
 #pragma unroll
             for (int i = 0; i < TM / 32; ++i) tma_load_3d(a + i * 4096, &tmA, &raw_full[s], m0 + 32 * i, k0, pa);
           } else {
@@ -664,8 +667,8 @@ gemm_tc3_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t dbh = p.tb ? make_desc(b_hi + k * b_step) : make_desc_mn(b_hi + k * b_step);
             const uint64_t dbl = p.tb ? make_desc(b_lo + k * b_step) : make_desc_mn(b_lo + k * b_step);
             const uint32_t acc0 = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_tf32(tmem_d, dal, dbh, idesc, acc0);
-            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            if (!p.a_bf16) umma_tf32(tmem_d, dal, dbh, idesc, acc0);
+            umma_tf32(tmem_d, dah, dbl, idesc, p.a_bf16 ? acc0 : 1u);
             umma_tf32(tmem_d, dah, dbh, idesc, 1u);
           }
           umma_commit(&raw_empty[s]);
@@ -677,19 +680,47 @@ gemm_tc3_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp >= T_EPI_WARPS) {
     // ===== split: hi in place, lo into the LO ring =====
     const int ctid = threadIdx.x - T_EPI_WARPS * 32;
-    const int per_thread = (slab_bytes >> 4) / (T_CONV_WARPS * 32);     // slabs are multiples of 4,096 bytes
+    // fp32 A: the whole slab [A | B] is split; bf16 A: only B is, A is expanded (slabs are multiples of 4,096 bytes)
+    const int first = p.a_bf16 ? (A_BYTES >> 4) / (T_CONV_WARPS * 32) : 0;
+    const int per_thread = (slab_bytes >> 4) / (T_CONV_WARPS * 32);
+    // bf16 A: chunk c of the dense 128 x 64-byte tile = 8 consecutive k of row c / 4
+    const int brow = ctid >> 2, boc = ctid & 3;
+    const uint32_t boff0 = sw_off(brow, boc * 8), boff1 = sw_off(brow, boc * 8 + 4);   // + 8,192 for row + 64
     long it = 0;
     for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = static_cast<int>(it % p.raw_stages), l = static_cast<int>(it % p.lo_stages);
         mbar_wait(&raw_full[s], static_cast<uint32_t>(it / p.raw_stages) & 1u);
         mbar_wait(&lo_empty[l], (static_cast<uint32_t>(it / p.lo_stages) & 1u) ^ 1u);
+        if (p.a_bf16) {
+          // bf16 -> fp32 is a 16-bit shift and exact in TF32.  The packed tile sits in the upper half of the
+          // region its expansion fills, so every split thread reads its two chunks, all of them meet at a
+          // named barrier, then they write.
+          const uint32_t abase = raw0 + s * slab_bytes;
+          uint32_t w[2][4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 v = lds128(abase + A_BYTES / 2 + (ctid + u * T_CONV_WARPS * 32) * 16);
+            w[u][0] = __float_as_uint(v.x); w[u][1] = __float_as_uint(v.y);
+            w[u][2] = __float_as_uint(v.z); w[u][3] = __float_as_uint(v.w);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(T_CONV_WARPS * 32) : "memory");
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            sts128(abase + boff0 + u * 8192,
+                   make_float4(__uint_as_float(w[u][0] << 16), __uint_as_float(w[u][0] & 0xffff0000u),
+                               __uint_as_float(w[u][1] << 16), __uint_as_float(w[u][1] & 0xffff0000u)));
+            sts128(abase + boff1 + u * 8192,
+                   make_float4(__uint_as_float(w[u][2] << 16), __uint_as_float(w[u][2] & 0xffff0000u),
+                               __uint_as_float(w[u][3] << 16), __uint_as_float(w[u][3] & 0xffff0000u)));
+          }
+        }
         const uint32_t src = raw0 + s * slab_bytes + ctid * 16, dst = lo0 + l * slab_bytes + ctid * 16;
         // four 16-byte chunks in flight per thread, two split warps per scheduler: the shared-memory load
         // latency was the whole cost of this pass with one warp per scheduler (ncu: every split warp always
         // busy, 40 % of its samples on the short scoreboard)
 #pragma unroll 1
-        for (int c0 = 0; c0 < per_thread; c0 += 4) {
+        for (int c0 = first; c0 < per_thread; c0 += 4) {
           float4 v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -818,8 +849,23 @@ static CUresult encode_3d(EncodeTiledFn encode, CUtensorMap* map, const float* b
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
+// bf16 matrix (outer x inner, pitch ld) per problem, dense (unswizzled) box {32, box_outer, 1}
+static CUresult encode_3d_bf16(EncodeTiledFn encode, CUtensorMap* map, const void* base, int inner, int outer, int ld,
+                               long stride, int batch, int box_outer) {
+  const bool batched = stride != 0 && batch > 1;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer),
+                              static_cast<cuuint64_t>(batched ? batch : 1)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2,
+                                 static_cast<cuuint64_t>(batched ? stride : static_cast<long>(ld) * outer) * 2};
+  const cuuint32_t box[3] = {32, static_cast<cuuint32_t>(box_outer), 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 // Returns 0 on launch, -100 when this variant does not take the problem (the caller falls back).
-static int launch_tma(int ta, int tb, int M, int N, int K, const float* A, int lda, long sa, const float* B, int ldb,
+static int launch_tma(int ta, int tb, int M, int N, int K, const void* A, int a_bf16, int lda, long sa, const float* B, int ldb,
                       long sb, void* C, int c_bf16, int ldc, long sc, int batch, float alpha, const float* alpha_dev,
                       const float* col_sub, cudaStream_t st) {
   EncodeTiledFn encode = encode_fn();
@@ -828,6 +874,7 @@ static int launch_tma(int ta, int tb, int M, int N, int K, const float* A, int l
   p.C = static_cast<float*>(C);
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.sc = sc;
   p.ta = ta ? 1 : 0; p.tb = tb ? 1 : 0;
+  p.a_bf16 = a_bf16;
   p.a_batched = (sa != 0 && batch > 1) ? 1 : 0;
   p.b_batched = (sb != 0 && batch > 1) ? 1 : 0;
   // N tiles of at most 224 columns: five slabs (three raw, two lo) fit the SM, so the split of slab kb + 1
@@ -850,8 +897,10 @@ static int launch_tma(int ta, int tb, int M, int N, int K, const float* A, int l
   const int dyn = (p.raw_stages + p.lo_stages) * slab + extra;
   CUtensorMap tmA, tmB;
   // A: ta = 0 stored M x K (K-major box {32 k, 128 rows}); ta = 1 stored K x M (MN-major boxes {32 rows, 32 k})
-  if ((ta ? encode_3d(encode, &tmA, A, M, K, lda, sa, batch, 32, true) : encode_3d(encode, &tmA, A, K, M, lda, sa, batch, TM, false)) !=
-      CUDA_SUCCESS)
+  const float* Af = static_cast<const float*>(A);
+  if ((a_bf16 ? encode_3d_bf16(encode, &tmA, A, K, M, lda, sa, batch, TM)
+              : ta ? encode_3d(encode, &tmA, Af, M, K, lda, sa, batch, 32, true)
+                   : encode_3d(encode, &tmA, Af, K, M, lda, sa, batch, TM, false)) != CUDA_SUCCESS)
     return -100;
   // B: tb = 1 stored N x K (K-major box {32 k, BN rows}); tb = 0 stored K x N (MN-major boxes)
   if ((tb ? encode_3d(encode, &tmB, B, K, N, ldb, sb, batch, bn, false) : encode_3d(encode, &tmB, B, N, K, ldb, sb, batch, 32, true)) !=
@@ -899,8 +948,8 @@ extern "C" int basd_gemm_tc3_batched_ex(int ta, int tb, int M, int N, int K, con
   const int a_bf16 = a_dtype == BASD_DTYPE_BF16;
   if (a_bf16 && (ta || (K & 7) || (lda & 7) || (sa & 7))) return -3;
   if (batch > 65535) return -4;
-  if (!a_bf16 && !std::getenv("BASD_TC3_NO_TMA")) {
-    const int e = tc3::launch_tma(ta, tb, M, N, K, static_cast<const float*>(A), lda, sa, B, ldb, sb, C,
+  if (!std::getenv("BASD_TC3_NO_TMA")) {
+    const int e = tc3::launch_tma(ta, tb, M, N, K, A, a_bf16, lda, sa, B, ldb, sb, C,
                                   c_dtype == BASD_DTYPE_BF16, ldc, sc, batch, alpha, alpha_dev, col_sub,
                                   (cudaStream_t)stream);
     if (e != -100) return e;
