@@ -98,10 +98,15 @@ if os.path.exists(ll):
     open(os.path.join(dst, f"{tag}_launches_c2_b256.csv"), "w").write(open(ll).read())
 traffic = {}
 recs_all = []
-for part in ("", "_jacobi_proc", "_jacobi_kxk", "_chol_reg", "_stepk"):
+# later parts are later captures: a kernel captured again replaces its earlier records; kernels that no longer
+# exist in the library are dropped
+RETIRED = ("tc3::gemm_tc3_kernel", "colsum_partial_bf16x8_kernel", "colsum_reduce_kernel")
+for part in ("", "_jacobi_proc", "_jacobi_kxk", "_chol_reg", "_stepk", "_final"):
     p = os.path.join(src, f"{tag}_full{part}_raw.csv")
     if os.path.exists(p):
-        recs_all += full_pages(p)
+        new = [r for r in full_pages(p) if not r["kernel"].startswith(RETIRED)]
+        names = {r["kernel"] for r in new}
+        recs_all = [r for r in recs_all if r["kernel"] not in names] + new
 for part in ("step",):
     if not recs_all:
         continue
@@ -114,7 +119,8 @@ for part in ("step",):
             best[r["kernel"]] = r
     lines += ["## `--set full` capture of the whole step: the longest launch of each kernel (B = 256), kernels "
               "above 0.03 ms (statistics + selector from the whole-step capture, which ran into its time limit after 129 "
-              "launches; the rest from targeted captures: `tools/gpu_profile2.sh`)", ""]
+              "launches; the rest from targeted captures: `tools/gpu_profile2.sh`; kernels changed after those "
+              "captures -- GEMM, token Gram, fp64 rotation, cluster Jacobi -- re-captured by `tools/gpu_profile3.sh`)", ""]
     for k, r in sorted(best.items(), key=lambda kv: -fnum(kv[1]["gpu__time_duration.sum"])):
         if fnum(r["gpu__time_duration.sum"]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(r["gpu__time_duration.sum"][1], 1.0) < 0.03:
             continue
@@ -138,7 +144,7 @@ open(os.path.join(dst, f"{tag}_ncu_summary.md"), "w").write("\n".join(lines) + "
 entry = {"basd_mix_interp": "mix_interp_kernel", "basd_weight_grad": "weight_grad_onepass_kernel",
          "basd_token_gram_tc": "tc::token_gram_tc_kernel", "basd_jacobi_rows[procrustes]": "jacobi_rows_oe8_kernel<16, 13>",
          "basd_jacobi_rows[eig]": "oe8::jacobi_rows_oe8_cluster_kernel", "basd_jacobi_rows[kxk]": "jacobi_rows_oe8_split_kernel",
-         "basd_pivoted_cholesky": "pivoted_cholesky_reg_kernel"}
+         "basd_pivoted_cholesky": "pivoted_cholesky_reg_kernel", "basd_gemm_tc3_batched": "tc3::gemm_tc3_tma_kernel"}
 tj = {}
 for e, k in entry.items():
     for name, rec in traffic.items():
