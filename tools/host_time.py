@@ -1,10 +1,11 @@
-"""Host enqueue time vs GPU time per step (is the step launch-bound?)."""
+"""Host enqueue time vs GPU time per step (is the step launch-bound?).  python tools/host_time.py [workload] [batch]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import basd_b200.synthetic as syn
 import bench
-work = syn.scaled(syn.WORKLOADS["c2"], 256)
+key = sys.argv[1] if len(sys.argv) > 1 else "c2"
+work = syn.scaled(syn.WORKLOADS[key], int(sys.argv[2]) if len(sys.argv) > 2 else 256)
 dev = torch.device("cuda", 0)
 mod = bench.build_module(work, dev)
 logits, targets, st, te, at = syn.make_inputs_fast(work, seed=0, device=dev)

@@ -144,7 +144,7 @@ open(os.path.join(dst, f"{tag}_ncu_summary.md"), "w").write("\n".join(lines) + "
 entry = {"basd_mix_interp": "mix_interp_kernel", "basd_weight_grad": "weight_grad_onepass_kernel",
          "basd_token_gram_tc": "tc::token_gram_tc_kernel", "basd_jacobi_rows[procrustes]": "jacobi_rows_oe8_kernel<16, 13>",
          "basd_jacobi_rows[eig]": "oe8::jacobi_rows_oe8_cluster_kernel", "basd_jacobi_rows[kxk]": "jacobi_rows_oe8_split_kernel",
-         "basd_pivoted_cholesky": "pivoted_cholesky_reg_kernel", "basd_gemm_tc3_batched": "tc3::gemm_tc3_tma_kernel"}
+         "basd_pivoted_cholesky": "pivoted_cholesky_reg_kernel"}   # (the GEMM entries aggregate 25 + 5 launches of different shapes: no per-launch figure)
 tj = {}
 for e, k in entry.items():
     for name, rec in traffic.items():
