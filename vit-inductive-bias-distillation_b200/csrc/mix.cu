@@ -374,25 +374,31 @@ weight_grad_onepass_kernel(LayerPtrs layers, int L, int E, const float* __restri
 }
 
 // d_weights[i,l] = sum_slices partial + sum_{b,n} gw[i,b,n] * resample(rows[l,b,:])[n]
-__global__ void weight_grad_finish_kernel(const float* __restrict__ partial, int slices,
-                                          const float* __restrict__ gw,
-                                          const float* __restrict__ rows, int E, int L, int B,
-                                          int n_rows, int n_dst, float gw_scale,
-                                          const float* __restrict__ gw_scale_dev,
-                                          float* __restrict__ d_weights) {
+// One CTA of 1,024 threads per (l, i): thread (tx, ty) owns token n = tx (+ 256, ...) -- its two resampling
+// taps are computed once -- and walks the samples b = ty, ty + 4, ...: coalesced along n, no per-element
+// division (the first version's flat index cost a div / mod and a tap evaluation per element: 0.11 ms for
+// 50,176 products per CTA).
+__global__ void __launch_bounds__(1024)
+weight_grad_finish_kernel(const float* __restrict__ partial, int slices,
+                          const float* __restrict__ gw,
+                          const float* __restrict__ rows, int E, int L, int B,
+                          int n_rows, int n_dst, float gw_scale,
+                          const float* __restrict__ gw_scale_dev,
+                          float* __restrict__ d_weights) {
   __shared__ float red[32];
   const int l = blockIdx.x, i = blockIdx.y;
+  const int tx = threadIdx.x & 255, ty = threadIdx.x >> 8;
   float s = 0.f, t = 0.f;
   for (int sl = threadIdx.x; sl < slices; sl += blockDim.x) t += partial[((long)sl * L + l) * E + i];
-  for (long idx = threadIdx.x; idx < (long)B * n_dst; idx += blockDim.x) {
-    const int n = idx % n_dst;
-    const int b = idx / n_dst;
+  for (int n = tx; n < n_dst; n += 256) {
     int lo, hi;
     float f;
     taps(n, n_rows, n_dst, lo, hi, f);
-    const float* r = rows + ((long)l * B + b) * n_rows;
-    const float v = r[lo] + f * (r[hi] - r[lo]);
-    s = fmaf(gw[((long)i * B + b) * n_dst + n], v, s);
+    for (int b = ty; b < B; b += 4) {
+      const float* r = rows + ((long)l * B + b) * n_rows;
+      const float v = r[lo] + f * (r[hi] - r[lo]);
+      s = fmaf(gw[((long)i * B + b) * n_dst + n], v, s);
+    }
   }
   if (gw_scale_dev) gw_scale *= *gw_scale_dev;
   s = block_sum(fmaf(gw_scale, s, t), red);
@@ -585,7 +591,7 @@ extern "C" int basd_weight_grad(const void* const* teacher_layers, int L, int E,
       weight_grad_onepass_kernel<float, 4, LC, false><<<g1, 256, 0, ST>>>(lp, L, E, Z, B, n_src, n_dst, D, partial);
     BASD_LAUNCH_CHECK();
     dim3 fg(L, E);
-    weight_grad_finish_kernel<<<fg, 256, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_rows, n_dst, gw_scale,
+    weight_grad_finish_kernel<<<fg, 1024, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_rows, n_dst, gw_scale,
                                                  gw_scale_dev, d_weights);
     BASD_LAUNCH_CHECK();
     return 0;
@@ -597,7 +603,7 @@ extern "C" int basd_weight_grad(const void* const* teacher_layers, int L, int E,
     weight_grad_kernel<float><<<grid, 256, 0, ST>>>(lp, E, Z, B, n_src, n_dst, D, partial);
   BASD_LAUNCH_CHECK();
   dim3 fgrid(L, E);
-  weight_grad_finish_kernel<<<fgrid, 256, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_rows, n_dst,
+  weight_grad_finish_kernel<<<fgrid, 1024, 0, ST>>>(partial, slices, gw, rows, E, L, B, n_rows, n_dst,
                                                    gw_scale, gw_scale_dev, d_weights);
   BASD_LAUNCH_CHECK();
   return 0;

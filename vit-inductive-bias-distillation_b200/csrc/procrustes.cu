@@ -235,8 +235,27 @@ procrustes_grad_prep_kernel(float* __restrict__ YA, float* __restrict__ YB,
   float* yb = YB ? YB + (long)s * stride_y : nullptr;
   if (!ya && !yb) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const bool vec = ((N | ldy) & 3) == 0 && (stride_y & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(YA) | reinterpret_cast<uintptr_t>(YB)) & 15) == 0;
   for (int r = warp; r < N; r += nw) {
     const float sc = 2.f * sqrtf(w[(long)s * N + r]);
+    if (vec) {                                        // 128-bit read-modify-write of the row
+      for (int c = 4 * lane; c < N; c += 128) {
+        const float4 id = make_float4(r == c ? 1.f : 0.f, r == c + 1 ? 1.f : 0.f, r == c + 2 ? 1.f : 0.f,
+                                      r == c + 3 ? 1.f : 0.f);
+        if (ya) {
+          float4* q = reinterpret_cast<float4*>(ya + (long)r * ldy + c);
+          const float4 v = *q;
+          *q = make_float4(sc * (id.x - v.x), sc * (id.y - v.y), sc * (id.z - v.z), sc * (id.w - v.w));
+        }
+        if (yb) {
+          float4* q = reinterpret_cast<float4*>(yb + (long)r * ldy + c);
+          const float4 v = *q;
+          *q = make_float4(sc * (id.x - v.x), sc * (id.y - v.y), sc * (id.z - v.z), sc * (id.w - v.w));
+        }
+      }
+      continue;
+    }
     for (int c = lane; c < N; c += 32) {
       const float id = (r == c) ? 1.f : 0.f;
       if (ya) ya[(long)r * ldy + c] = sc * (id - ya[(long)r * ldy + c]);
