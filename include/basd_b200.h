@@ -225,6 +225,9 @@ int basd_weight_grad(const void* const* teacher_layers, int L, int E, const floa
  * kind::tf32 MMAs per K step accumulate in TMEM ("3xTF32").  ta = 0: A stored M x K,
  * ta = 1: stored K x M;  tb = 0: B stored K x N, tb = 1: stored N x K.  Pointers 16-byte
  * aligned; M, N, K, pitches and strides multiples of 4 (basd_gemm_tc3_supported tells).
+ * Operands are fetched by TMA (tensor maps over (inner, outer, batch), encoded per call on the
+ * host): a stride of 0 shares an operand across the batch.  Returns 0, -3 (alignment / shape
+ * rule), -4 (batch > 65535) or -5 (the driver refused the tensor map).
  * Replaces torch.bmm (relational.py:47) and the matmuls of linalg.svd's backward for the
  * per-sample Procrustes products. */
 int basd_gemm_tc3_supported(int M, int N, int K, int lda, int ldb, int ldc, long sa, long sb,
