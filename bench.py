@@ -416,7 +416,7 @@ def run_b200(args):
 
     # the first upload (1.1 GB over PCIe, ~22 ms) cannot overlap anything: run enough steps that the
     # pipeline fill is a small share of the wall-clock window, as it is in a training loop
-    e2e_steps = max(12, args.steps)
+    e2e_steps = max(24, args.steps)                      # enough steps that one host hiccup does not move the mean
     e2e_run(2)
     barrier()
     t0 = time.perf_counter()
