@@ -92,3 +92,46 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     assert slices > 0 and slices % 148 == 0              # grid sized in multiples of the SM count
     assert ws_bytes >= 768 * 768 * 4                     # at least one D x D fp32 partial
     assert ok in (0, 1)
+
+
+def header_prototypes():
+    """name -> list of ctypes kinds ('p', 'i', 'l', 'f', 'd') parsed from the header's prototypes."""
+    text = open(os.path.join(ROOT, "include", "basd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|long)\s+(basd_\w+)\s*\(([^)]*)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), " ".join(m.group(2).split())
+        kinds = []
+        if params not in ("", "void"):
+            for prm in params.split(","):
+                prm = prm.strip()
+                if "*" in prm:
+                    kinds.append("p")
+                elif re.match(r"(const\s+)?double\b", prm):
+                    kinds.append("d")
+                elif re.match(r"(const\s+)?float\b", prm):
+                    kinds.append("f")
+                elif re.match(r"(const\s+)?long\b", prm):
+                    kinds.append("l")
+                elif re.match(r"(const\s+)?int\b", prm):
+                    kinds.append("i")
+                else:
+                    raise AssertionError(f"{name}: parameter type not understood: {prm!r}")
+        protos[name] = kinds
+    return protos
+
+
+def test_binding_argument_types_match_the_header():
+    """Every ctypes signature in _native.py has the arity and the scalar kinds of the prototype in
+    include/basd_b200.h (a drifted binding would corrupt a call silently: ctypes checks nothing)."""
+    from basd_b200 import _native as nat
+    kind = {ctypes.c_void_p: "p", ctypes.c_int: "i", ctypes.c_long: "l", ctypes.c_float: "f",
+            ctypes.c_double: "d"}
+    protos = header_prototypes()
+    table = dict(nat._SIG)
+    table.update({k: v[0] for k, v in nat._OPTIONAL.items()})
+    assert len(table) >= 40
+    for name, argtypes in table.items():
+        assert name in protos, f"{name} bound but no prototype parsed"
+        got = [kind[t] for t in argtypes]
+        assert got == protos[name], f"{name}: binding {got} != header {protos[name]}"
