@@ -85,8 +85,6 @@ int launch_gram_reduce(const float* partial, int slices, int D, int tile, float*
                        float coef = 0.f);
 int launch_colsum_fold(const float* partial, int slices, int D, float* out, const float* mu0, float coef,
                        cudaStream_t st);
-int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial /* >= 64*D floats */,
-                       float* out, cudaStream_t st, const float* mu0 = nullptr);
 
 // jacobi_oe8.cu: register-resident Jacobi with eight rows per 16-lane group (<= 224 x 224 active);
 // returns -100 when the shape does not fit.

@@ -417,52 +417,6 @@ __global__ void colsum_partial_kernel(const T* __restrict__ X, long rows, int D,
     partial[(long)blockIdx.y * D + d] = tot;
   }
 }
-// bf16, D % 8 == 0: every thread owns 8 adjacent columns (one 128-bit load per row), a warp
-// covers 256 columns, the 8 warps of a block stride over the rows of the slice with four loads in
-// flight each -- an HBM-speed pass (the scalar kernel above reached 1.1 TB/s of 6.5).
-__global__ void __launch_bounds__(256)
-colsum_partial_bf16x8_kernel(const __nv_bfloat16* __restrict__ X, long rows, int D,
-                             long rows_per_slice, float* __restrict__ partial,
-                             const float* __restrict__ mu0) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = (blockIdx.x * 32 + lane) * 8;
-  const long r_begin = (long)blockIdx.y * rows_per_slice;
-  const long r_end = min(rows, r_begin + rows_per_slice);
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (c0 < D) {
-    float m[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = mu0 ? mu0[c0 + i] : 0.f;
-    long r = r_begin + warp;
-    for (; r + 24 < r_end; r += 32) {
-      float v[4][8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) load8(X + (r + 8 * u) * D + c0, v[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += v[u][i] - m[i];
-    }
-    for (; r < r_end; r += 8) {
-      float v[8];
-      load8(X + r * D + c0, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += v[i] - m[i];
-    }
-  }
-  __shared__ float red[8][256 + 8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
-  __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < D) {
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[w][threadIdx.x];
-    partial[(long)blockIdx.y * D + c] = tot;
-  }
-}
-
 __global__ void colsum_reduce_kernel(const float* __restrict__ partial, int slices, int D,
                                      float* __restrict__ out) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -570,32 +524,6 @@ __global__ void colsum_fold_kernel(const float* __restrict__ partial, int slices
 int launch_colsum_fold(const float* partial, int slices, int D, float* out, const float* mu0, float coef,
                        cudaStream_t st) {
   colsum_fold_kernel<<<(D + 127) / 128, 128, 0, st>>>(partial, slices, D, out, mu0, coef);
-  BASD_LAUNCH_CHECK();
-  return 0;
-}
-
-int launch_colsum_bf16(const void* tokens, long rows, int D, float* partial, float* out,
-                       cudaStream_t st, const float* mu0) {
-  int cs = (int)((rows + 4095) / 4096);
-  if (cs > 64) cs = 64;
-  if (cs < 1) cs = 1;
-  if ((D & 7) == 0 && (reinterpret_cast<uintptr_t>(tokens) & 15) == 0) {
-    cs = (int)((rows + 255) / 256);                      // <= 64 slices of >= 256 rows (workspace: 64 * D)
-    if (cs > 64) cs = 64;
-    if (cs < 1) cs = 1;
-    const long per = (rows + cs - 1) / cs;
-    dim3 vgrid((D + 255) / 256, cs);
-    colsum_partial_bf16x8_kernel<<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)tokens, rows, D, per,
-                                                        partial, mu0);
-    colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(partial, cs, D, out);
-    BASD_LAUNCH_CHECK();
-    return 0;
-  }
-  const long per = (rows + cs - 1) / cs;
-  dim3 cgrid((D + 31) / 32, cs);
-  colsum_partial_kernel<__nv_bfloat16><<<cgrid, 256, 0, st>>>((const __nv_bfloat16*)tokens, rows, D,
-                                                              per, partial, mu0);
-  colsum_reduce_kernel<<<(D + 127) / 128, 128, 0, st>>>(partial, cs, D, out);
   BASD_LAUNCH_CHECK();
   return 0;
 }

@@ -314,6 +314,7 @@ static int plan_slices(long rows, int D) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long slices = sms / upper;
+  if (slices > 64) slices = 64;                         // the column-sum partials have 64 slots (D = 128 only)
   const long kblocks = (rows + BK - 1) / BK;
   if (slices > kblocks) slices = kblocks;
   if (slices < 1) slices = 1;
@@ -378,19 +379,14 @@ extern "C" int basd_token_gram_tc(const void* tokens, long rows, int D, const fl
   // column sums ride on the tensor core (diagonal tiles); with a shift the kernel's accumulator is
   // sum x - Mc mu0: the slices' partials are folded by the column-sum reduce kernel, then d = sum (x - mu0)
   // needs + (Mc - M) mu0, applied by the Gram reduce below together with its own conversion
-  const bool fused_cs = colsum != nullptr && slices <= 64;
+  const bool fused_cs = colsum != nullptr;
   BASD_CUDA(cudaFuncSetAttribute(token_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SMEM_BYTES));
   dim3 grid(tiles * (tiles + 1) / 2, slices);
   token_gram_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tmap, tmap_mu, mu0 ? 1 : 0, part_g, fused_cs ? part_c : nullptr, D,
                                                       rows, per);
   BASD_LAUNCH_CHECK();
-  if (colsum) {
-    if (fused_cs) {
-      if (int e = launch_colsum_fold(part_c, slices, D, colsum, mu0, static_cast<float>(corrected - rows), st)) return e;
-    } else if (int e = launch_colsum_bf16(tokens, rows, D, part_c, colsum, st, mu0)) {
-      return e;
-    }
-  }
+  if (fused_cs)
+    if (int e = launch_colsum_fold(part_c, slices, D, colsum, mu0, static_cast<float>(corrected - rows), st)) return e;
   return launch_gram_reduce(part_g, slices, D, TILE, gram, st, mu0, colsum, static_cast<float>(corrected - rows));
 }
